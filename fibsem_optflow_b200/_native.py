@@ -1,0 +1,375 @@
+"""ctypes binding of libtvl1_b200.so (the C ABI in include/tvl1_b200.h).
+
+There is NO fallback: if the shared library is missing, or no CUDA device is present when
+a compute entry point is called, this module raises.  Nothing here imports oracle/.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "csrc", "libtvl1_b200.so")
+
+MAX_LEVELS = 32
+MAX_WARPS = 64
+
+
+class Tvl1Error(RuntimeError):
+    pass
+
+
+class Params(C.Structure):
+    _fields_ = [
+        ("tau", C.c_double), ("lambda_", C.c_double), ("theta", C.c_double),
+        ("epsilon", C.c_double), ("scale_step", C.c_double), ("gamma", C.c_double),
+        ("nscales", C.c_int), ("warps", C.c_int), ("iterations", C.c_int),
+        ("inner_iterations", C.c_int), ("outer_iterations", C.c_int),
+        ("median_filtering", C.c_int), ("use_initial_flow", C.c_int),
+        ("reserved", C.c_int * 3),
+    ]
+
+
+class Stats(C.Structure):
+    _fields_ = [
+        ("levels", C.c_int), ("warps", C.c_int),
+        ("width", C.c_int * MAX_LEVELS), ("height", C.c_int * MAX_LEVELS),
+        ("iters", C.c_int * (MAX_LEVELS * MAX_WARPS)),
+        ("outer", C.c_int * (MAX_LEVELS * MAX_WARPS)),
+        ("total_iterations", C.c_longlong), ("px_iterations", C.c_longlong),
+        ("algorithmic_bytes", C.c_double),
+        ("ms_total", C.c_float), ("ms_pyramid", C.c_float), ("ms_warp", C.c_float),
+        ("ms_iterate", C.c_float), ("ms_median", C.c_float), ("ms_other", C.c_float),
+        ("ms_iterate_level", C.c_float * MAX_LEVELS),
+        ("launches", C.c_longlong),
+    ]
+
+    def iters_array(self):
+        a = np.ctypeslib.as_array(self.iters)[: self.levels * self.warps]
+        return a.reshape(self.levels, self.warps).copy()
+
+    def outer_array(self):
+        a = np.ctypeslib.as_array(self.outer)[: self.levels * self.warps]
+        return a.reshape(self.levels, self.warps).copy()
+
+    def level_sizes(self):
+        return [(self.width[i], self.height[i]) for i in range(self.levels)]
+
+
+# every symbol include/tvl1_b200.h declares (checked by tests/test_abi.py)
+EXPORTS = [
+    "tvl1_version", "tvl1_last_error", "tvl1_default_params", "tvl1_create", "tvl1_destroy",
+    "tvl1_set_params", "tvl1_set_timing", "tvl1_calc_u8", "tvl1_calc_u8_host",
+    "tvl1_mask_flow_u8", "tvl1_sample_matches", "tvl1_k_convert_u8", "tvl1_k_resize",
+    "tvl1_k_centered_gradient", "tvl1_k_warp", "tvl1_k_iterate", "tvl1_k_median5",
+    "tvl1_pyramid_sizes", "tvl1_glibc_rand", "tvl1_dev_count", "tvl1_dev_alloc", "tvl1_dev_free",
+    "tvl1_dev_memset", "tvl1_dev_h2d", "tvl1_dev_d2h", "tvl1_dev_sync",
+    "tvl1_host_alloc_pinned", "tvl1_host_free_pinned",
+]
+
+_lib = None
+_vp = C.c_void_p
+_sz = C.c_size_t
+
+
+def lib():
+    """Loads the library; raises if it has not been built (python fibsem_optflow_b200/csrc/build.py)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(SO_PATH):
+        raise Tvl1Error(
+            "%s is missing: build it with `python fibsem_optflow_b200/csrc/build.py` "
+            "(there is no CPU fallback)" % SO_PATH)
+    L = C.CDLL(SO_PATH)
+    L.tvl1_version.restype = C.c_char_p
+    L.tvl1_last_error.restype = C.c_char_p
+    L.tvl1_default_params.argtypes = [C.POINTER(Params)]
+    L.tvl1_default_params.restype = None
+    L.tvl1_create.argtypes = [C.POINTER(Params), C.c_int, C.POINTER(_vp)]
+    L.tvl1_destroy.argtypes = [_vp]
+    L.tvl1_destroy.restype = None
+    L.tvl1_set_params.argtypes = [_vp, C.POINTER(Params)]
+    L.tvl1_set_timing.argtypes = [_vp, C.c_int]
+    L.tvl1_calc_u8.argtypes = [_vp, _vp, _sz, _vp, _sz, C.c_int, C.c_int, _vp, _vp, _sz, _vp,
+                               C.POINTER(Stats)]
+    L.tvl1_calc_u8_host.argtypes = [_vp, _vp, _sz, _vp, _sz, C.c_int, C.c_int, _vp, _vp, _sz,
+                                    C.POINTER(Stats)]
+    L.tvl1_mask_flow_u8.argtypes = [_vp, _vp, _sz, C.c_int, C.c_int, _vp, _vp, _sz, _vp]
+    L.tvl1_sample_matches.argtypes = [_vp, _vp, _sz, _vp, _sz, _vp, _vp, _sz, C.c_int, C.c_int,
+                                      C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int,
+                                      C.c_longlong, _vp, _vp, _vp, _vp, _vp, _vp,
+                                      C.POINTER(C.c_int), _vp]
+    L.tvl1_k_convert_u8.argtypes = [_vp, _sz, C.c_int, C.c_int, _vp, C.c_int, _vp]
+    L.tvl1_k_resize.argtypes = [_vp, C.c_int, C.c_int, C.c_int, _vp, C.c_int, C.c_int, C.c_int,
+                                C.c_double, C.c_float, _vp]
+    L.tvl1_k_centered_gradient.argtypes = [_vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp]
+    L.tvl1_k_warp.argtypes = [_vp] * 6 + [C.c_int, C.c_int, C.c_int] + [_vp] * 5
+    L.tvl1_k_iterate.argtypes = [_vp] * 10 + [C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
+                                              C.c_float, C.c_int, _vp, _vp]
+    L.tvl1_k_median5.argtypes = [_vp, C.c_int, C.c_int, C.c_int, _vp, _vp]
+    L.tvl1_pyramid_sizes.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, _vp, _vp]
+    L.tvl1_glibc_rand.argtypes = [C.c_longlong, C.c_longlong, C.c_int, _vp]
+    L.tvl1_dev_alloc.argtypes = [C.c_int, _sz, C.POINTER(_vp)]
+    L.tvl1_dev_free.argtypes = [C.c_int, _vp]
+    L.tvl1_dev_memset.argtypes = [_vp, C.c_int, _sz]
+    L.tvl1_dev_h2d.argtypes = [_vp, _vp, _sz]
+    L.tvl1_dev_d2h.argtypes = [_vp, _vp, _sz]
+    L.tvl1_dev_sync.argtypes = [C.c_int]
+    L.tvl1_host_alloc_pinned.argtypes = [_sz, C.POINTER(_vp)]
+    L.tvl1_host_free_pinned.argtypes = [_vp]
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc < 0:
+        raise Tvl1Error("tvl1 error %d: %s" % (rc, lib().tvl1_last_error().decode()))
+    return rc
+
+
+def device_count():
+    return lib().tvl1_dev_count()
+
+
+def require_device():
+    n = device_count()
+    if n <= 0:
+        raise Tvl1Error("no CUDA device visible; fibsem_optflow_b200 has no CPU path")
+    return n
+
+
+def default_params(**kw):
+    p = Params()
+    lib().tvl1_default_params(C.byref(p))
+    for k, v in kw.items():
+        k = {"lambda": "lambda_", "scaleStep": "scale_step", "useInitialFlow": "use_initial_flow",
+             "innerIterations": "inner_iterations", "outerIterations": "outer_iterations",
+             "medianFiltering": "median_filtering"}.get(k, k)
+        if not hasattr(p, k):
+            raise KeyError(k)
+        setattr(p, k, v)
+    return p
+
+
+def pyramid_sizes(w, h, nscales, scale_step):
+    ws = (C.c_int * (MAX_LEVELS + 1))()
+    hs = (C.c_int * (MAX_LEVELS + 1))()
+    n = check(lib().tvl1_pyramid_sizes(w, h, nscales, scale_step, ws, hs))
+    return [(ws[i], hs[i]) for i in range(n)]
+
+
+def glibc_rand(seed, skip, n):
+    out = np.zeros(n, np.int32)
+    check(lib().tvl1_glibc_rand(seed, skip, n, out.ctypes.data))
+    return out
+
+
+class DevBuf:
+    """A device allocation (tvl1_dev_alloc) with NumPy upload/download helpers."""
+
+    def __init__(self, nbytes, device=0):
+        self.device = device
+        self.nbytes = int(nbytes)
+        p = _vp()
+        check(lib().tvl1_dev_alloc(device, self.nbytes, C.byref(p)))
+        self.ptr = p.value
+
+    def free(self):
+        if self.ptr:
+            lib().tvl1_dev_free(self.device, self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+    def upload(self, arr):
+        arr = np.ascontiguousarray(arr)
+        assert arr.nbytes <= self.nbytes
+        check(lib().tvl1_dev_h2d(self.ptr, arr.ctypes.data, arr.nbytes))
+        return self
+
+    def download(self, shape, dtype):
+        out = np.empty(shape, dtype)
+        assert out.nbytes <= self.nbytes
+        check(lib().tvl1_dev_d2h(out.ctypes.data, self.ptr, out.nbytes))
+        return out
+
+    def zero(self):
+        check(lib().tvl1_dev_memset(self.ptr, 0, self.nbytes))
+        return self
+
+
+def pitch_of(w):
+    return (w + 31) // 32 * 32
+
+
+class Plane:
+    """A pitched fp32 device plane (pitch multiple of 32 floats, pad columns zeroed)."""
+
+    def __init__(self, h, w, device=0, data=None):
+        self.h, self.w, self.pitch = h, w, pitch_of(w)
+        self.buf = DevBuf(self.h * self.pitch * 4, device)
+        if data is None:
+            self.buf.zero()
+        else:
+            self.set(data)
+
+    @property
+    def ptr(self):
+        return self.buf.ptr
+
+    def set(self, data):
+        a = np.zeros((self.h, self.pitch), np.float32)
+        a[:, : self.w] = data
+        self.buf.upload(a)
+
+    def get(self):
+        return self.buf.download((self.h, self.pitch), np.float32)[:, : self.w].copy()
+
+
+class Solver:
+    """One solver handle on one device (tvl1_create .. tvl1_destroy)."""
+
+    def __init__(self, params=None, device=0, **kw):
+        require_device()
+        self.params = params if params is not None else default_params(**kw)
+        self.device = device
+        h = _vp()
+        check(lib().tvl1_create(C.byref(self.params), device, C.byref(h)))
+        self.handle = h.value
+        self.stats = Stats()
+
+    def close(self):
+        if getattr(self, "handle", None):
+            lib().tvl1_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_params(self, params):
+        check(lib().tvl1_set_params(self.handle, C.byref(params)))
+        self.params = params
+
+    def calc(self, I0, I1):
+        """Host uint8 images -> (u, v) host float32; H2D and D2H inside (tvl1_calc_u8_host)."""
+        I0 = np.ascontiguousarray(I0, np.uint8)
+        I1 = np.ascontiguousarray(I1, np.uint8)
+        if I0.ndim != 2 or I0.shape != I1.shape:
+            raise Tvl1Error("frames must be 2-D uint8 arrays of equal size")
+        h, w = I0.shape
+        u = np.empty((h, w), np.float32)
+        v = np.empty((h, w), np.float32)
+        check(lib().tvl1_calc_u8_host(self.handle, I0.ctypes.data, w, I1.ctypes.data, w, w, h,
+                                      u.ctypes.data, v.ctypes.data, w * 4, C.byref(self.stats)))
+        return u, v
+
+    def calc_device(self, d_f0, pitch0, d_f1, pitch1, w, h, d_u, d_v, pitch_out, stream=None):
+        check(lib().tvl1_calc_u8(self.handle, d_f0, pitch0, d_f1, pitch1, w, h, d_u, d_v,
+                                 pitch_out, stream, C.byref(self.stats)))
+
+    def mask_flow_device(self, d_f1, pitch1, w, h, d_u, d_v, pitch_out, stream=None):
+        check(lib().tvl1_mask_flow_u8(self.handle, d_f1, pitch1, w, h, d_u, d_v, pitch_out, stream))
+
+    def sample_matches_device(self, d_f0, pitch0, d_f1, pitch1, d_u, d_v, pitch_flow, w, h,
+                              roi0=(0, 0), roi1=(0, 0), scale=0.5, npoints=25, seed=-1,
+                              stream=None):
+        n = max(int(npoints), 1)
+        px, py, qx, qy, wg = (np.zeros(n, np.float64) for _ in range(5))
+        pos = np.zeros((n, 2), np.int32)
+        k = C.c_int(0)
+        check(lib().tvl1_sample_matches(self.handle, d_f0, pitch0, d_f1, pitch1, d_u, d_v,
+                                        pitch_flow, w, h, roi0[0], roi0[1], roi1[0], roi1[1],
+                                        scale, npoints, seed, px.ctypes.data, py.ctypes.data,
+                                        qx.ctypes.data, qy.ctypes.data, wg.ctypes.data,
+                                        pos.ctypes.data, C.byref(k), stream))
+        k = k.value
+        return px[:k], py[:k], qx[:k], qy[:k], wg[:k], pos[:k]
+
+    def sample_matches(self, f0, f1, u, v, **kw):
+        """Host arrays in, match arrays out (uploads the four planes)."""
+        f0 = np.ascontiguousarray(f0, np.uint8)
+        f1 = np.ascontiguousarray(f1, np.uint8)
+        u = np.ascontiguousarray(u, np.float32)
+        v = np.ascontiguousarray(v, np.float32)
+        h, w = f0.shape
+        b0 = DevBuf(f0.nbytes, self.device).upload(f0)
+        b1 = DevBuf(f1.nbytes, self.device).upload(f1)
+        bu = DevBuf(u.nbytes, self.device).upload(u)
+        bv = DevBuf(v.nbytes, self.device).upload(v)
+        try:
+            return self.sample_matches_device(b0.ptr, w, b1.ptr, w, bu.ptr, bv.ptr, w * 4, w, h, **kw)
+        finally:
+            for b in (b0, b1, bu, bv):
+                b.free()
+
+
+# ---- stage-level helpers (tests / profiling): host arrays in, host arrays out
+
+def k_convert_u8(img, device=0):
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape
+    src = DevBuf(img.nbytes, device).upload(img)
+    dst = Plane(h, w, device)
+    check(lib().tvl1_k_convert_u8(src.ptr, w, w, h, dst.ptr, dst.pitch, None))
+    check(lib().tvl1_dev_sync(device))
+    return dst.get()
+
+
+def k_resize(src, dw=None, dh=None, inv_scale=0.0, mul=1.0, device=0):
+    src = np.asarray(src, np.float32)
+    sh, sw = src.shape
+    if inv_scale > 0:   # resize(src, Size(), f, f): dsize = round-half-even(n * f)
+        dw, dh = int(np.rint(sw * inv_scale)), int(np.rint(sh * inv_scale))
+    s = Plane(sh, sw, device, src)
+    d = Plane(dh, dw, device)
+    check(lib().tvl1_k_resize(s.ptr, sw, sh, s.pitch, d.ptr, dw, dh, d.pitch, inv_scale, mul, None))
+    check(lib().tvl1_dev_sync(device))
+    return d.get()
+
+
+def k_centered_gradient(src, device=0):
+    src = np.asarray(src, np.float32)
+    h, w = src.shape
+    s = Plane(h, w, device, src)
+    dx, dy = Plane(h, w, device), Plane(h, w, device)
+    check(lib().tvl1_k_centered_gradient(s.ptr, w, h, s.pitch, dx.ptr, dy.ptr, None))
+    check(lib().tvl1_dev_sync(device))
+    return dx.get(), dy.get()
+
+
+def k_warp(I0, I1, I1x, I1y, u1, u2, device=0):
+    h, w = np.asarray(I0).shape
+    ins = [Plane(h, w, device, np.asarray(a, np.float32)) for a in (I0, I1, I1x, I1y, u1, u2)]
+    outs = [Plane(h, w, device) for _ in range(4)]
+    check(lib().tvl1_k_warp(*[p.ptr for p in ins], w, h, ins[0].pitch, *[p.ptr for p in outs], None))
+    check(lib().tvl1_dev_sync(device))
+    return tuple(p.get() for p in outs)   # I1wx, I1wy, grad, rho_c
+
+
+def k_iterate(I1wx, I1wy, grad, rho_c, u1, u2, p11, p12, p21, p22, l_t, theta, taut, n=1, device=0):
+    """n iterations; returns (u1,u2,p11,p12,p21,p22, errors[n])."""
+    h, w = np.asarray(u1).shape
+    consts = [Plane(h, w, device, np.asarray(a, np.float32)) for a in (I1wx, I1wy, grad, rho_c)]
+    state = [Plane(h, w, device, np.asarray(a, np.float32)) for a in (u1, u2, p11, p12, p21, p22)]
+    errs = np.zeros(max(n, 1), np.float64)
+    check(lib().tvl1_k_iterate(*[p.ptr for p in consts], *[p.ptr for p in state], w, h,
+                               state[0].pitch, l_t, theta, taut, n, errs.ctypes.data, None))
+    return tuple(p.get() for p in state) + (errs[:n],)
+
+
+def k_median5(src, device=0):
+    src = np.asarray(src, np.float32)
+    h, w = src.shape
+    s = Plane(h, w, device, src)
+    d = Plane(h, w, device)
+    check(lib().tvl1_k_median5(s.ptr, w, h, s.pitch, d.ptr, None))
+    check(lib().tvl1_dev_sync(device))
+    return d.get()

@@ -1,0 +1,763 @@
+// tvl1_engine.cu -- per-device solver handle, the pair-level driver loop and the C ABI
+// declared in include/tvl1_b200.h.  Replaces TVL1_solve (reference src/optflow.cpp:516-520),
+// which builds a fresh cv::cuda::OpticalFlowDual_TVL1 -- and all its buffers -- per call: here
+// the handle keeps one arena per device and re-uses it across pairs of the same size.
+//
+// There is no CPU fallback: every entry point runs CUDA kernels or fails with a status.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "tvl1_kernels.cuh"
+#include "tvl1_internal.h"
+
+namespace tvl1 {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CK(call)                                                                          \
+    do {                                                                                  \
+        cudaError_t e_ = (call);                                                          \
+        if (e_ != cudaSuccess)                                                            \
+            return fail(TVL1_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                        __FILE__, __LINE__);                                              \
+    } while (0)
+
+static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// ---------------------------------------------------------------- cubic table (A.4)
+
+static void cubic_coeffs(float x, float* c)
+{
+    // Keys bicubic, A = -0.75, evaluated in fp32 exactly as OpenCV's interpolateCubic does
+    const float A = -0.75f;
+    c[0] = ((A * (x + 1) - 5 * A) * (x + 1) + 8 * A) * (x + 1) - 4 * A;
+    c[1] = ((A + 2) * x - (A + 3)) * x * x + 1;
+    c[2] = ((A + 2) * (1 - x) - (A + 3)) * (1 - x) * (1 - x) + 1;
+    c[3] = 1.f - c[0] - c[1] - c[2];
+}
+
+static int upload_cubic_table(int device)
+{
+    static bool done[64] = {false};
+    if (device >= 0 && device < 64 && done[device]) return TVL1_OK;
+    float tab[128];
+    const float scale = 1.f / 32;
+    for (int i = 0; i < 32; i++) cubic_coeffs(i * scale, tab + 4 * i);
+    CK(cudaMemcpyToSymbol(c_cubic_tab, tab, sizeof(tab)));
+    if (device >= 0 && device < 64) done[device] = true;
+    return TVL1_OK;
+}
+
+// ---------------------------------------------------------------- pyramid geometry (A.2)
+
+static int scaled_size(int n, double f) { return (int)lrint((double)n * f); }   // round half even
+
+int pyramid_sizes(int w, int h, int nscales, double scale_step, int* ws, int* hs)
+{
+    if (nscales > TVL1_MAX_LEVELS) nscales = TVL1_MAX_LEVELS;
+    ws[0] = w;
+    hs[0] = h;
+    int used = nscales;
+    for (int s = 1; s < nscales; s++) {
+        ws[s] = scaled_size(ws[s - 1], scale_step);
+        hs[s] = scaled_size(hs[s - 1], scale_step);
+        if (ws[s] < 16 || hs[s] < 16) { used = s; break; }   // that level is built then dropped
+    }
+    return used;
+}
+
+// ---------------------------------------------------------------- launch helpers
+
+static inline dim3 grid2d(int w, int h, dim3 b) { return dim3(cdiv(w, b.x), cdiv(h, b.y)); }
+
+int launch_convert(const uint8_t* src, size_t pitch, int w, int h, float* dst, int dpitch, cudaStream_t st)
+{
+    dim3 b(32, 8);
+    dim3 g(cdiv(cdiv(w, 4), 32), cdiv(h, 8));
+    k_convert_u8<<<g, b, 0, st>>>(src, pitch, w, h, dst, dpitch);
+    CK(cudaGetLastError());
+    return TVL1_OK;
+}
+
+int launch_resize(const float* src, int sw, int sh, int sp, float* dst, int dw, int dh, int dp,
+                  double inv_scale, float mul, int apply_mul, cudaStream_t st)
+{
+    double inv_x, inv_y;
+    if (inv_scale > 0) { inv_x = inv_scale; inv_y = inv_scale; }
+    else { inv_x = (double)dw / sw; inv_y = (double)dh / sh; }
+    const double scale_x = 1. / inv_x, scale_y = 1. / inv_y;
+    dim3 b(32, 8);
+    k_resize<<<grid2d(dw, dh, b), b, 0, st>>>(src, sw, sh, sp, dst, dw, dh, dp, scale_x, scale_y, mul, apply_mul);
+    CK(cudaGetLastError());
+    return TVL1_OK;
+}
+
+int launch_gradient(const float* src, int w, int h, int pitch, float* dx, float* dy, cudaStream_t st)
+{
+    dim3 b(32, 8);
+    k_centered_gradient<<<grid2d(w, h, b), b, 0, st>>>(src, w, h, pitch, dx, dy);
+    CK(cudaGetLastError());
+    return TVL1_OK;
+}
+
+int launch_warp(const WarpArgs& a, cudaStream_t st)
+{
+    dim3 b(32, 8);
+    k_warp<<<grid2d(a.w, a.h, b), b, 0, st>>>(a);
+    CK(cudaGetLastError());
+    return TVL1_OK;
+}
+
+static const int ITER_NW = 4;
+
+// rows per strip: tall strips amortise the bottom-halo row, short ones keep small levels
+// spread over all 148 SMs
+static int iterate_rows(int w, int h)
+{
+    const int gx = cdiv(cdiv(w, TVL1_STRIP), ITER_NW);
+    const int target = 148 * 4;
+    if (gx * cdiv(h, 16) >= target) return 16;
+    if (gx * cdiv(h, 8) >= target) return 8;
+    return 4;
+}
+
+size_t iterate_max_blocks(int w, int h)
+{
+    return (size_t)cdiv(cdiv(w, TVL1_STRIP), ITER_NW) * cdiv(h, 4);
+}
+
+int launch_iterate(const IterArgs& a, cudaStream_t st)
+{
+    const int R = iterate_rows(a.w, a.h);
+    dim3 b(32, ITER_NW);
+    dim3 g(cdiv(cdiv(a.w, TVL1_STRIP), ITER_NW), cdiv(a.h, R));
+    switch (R) {
+        case 16: k_iterate<16, ITER_NW><<<g, b, 0, st>>>(a); break;
+        case 8: k_iterate<8, ITER_NW><<<g, b, 0, st>>>(a); break;
+        default: k_iterate<4, ITER_NW><<<g, b, 0, st>>>(a); break;
+    }
+    CK(cudaGetLastError());
+    return TVL1_OK;
+}
+
+int launch_median(const MedianArgs& a, int planes, cudaStream_t st)
+{
+    dim3 b(32, 8);
+    dim3 g(cdiv(a.w, 32), cdiv(a.h, 8), planes);
+    k_median5<<<g, b, 0, st>>>(a);
+    CK(cudaGetLastError());
+    return TVL1_OK;
+}
+
+// ---------------------------------------------------------------- handle
+
+struct Level {
+    int w, h, pitch;
+    float *I0, *I1, *u1, *u2;   // u1/u2: buffer [0] of the twin pair; [1] is shared scratch
+};
+
+}  // namespace tvl1
+
+using namespace tvl1;
+
+struct tvl1_handle {
+    int device = 0;
+    tvl1_params prm;
+    int inner = 30, outer = 10;
+    bool timing = false;
+    // arena
+    char* arena = nullptr;
+    size_t arena_bytes = 0;
+    int cap_w = 0, cap_h = 0, cap_scales = 0;
+    double cap_step = 0;
+    int nlevels = 0;
+    Level lv[TVL1_MAX_LEVELS];
+    float *I1x = nullptr, *I1y = nullptr, *I1wx = nullptr, *I1wy = nullptr, *grad = nullptr, *rho = nullptr;
+    float *u1x = nullptr, *u2x = nullptr;   // twin [1] of u, shared by all levels
+    float* p[4][2] = {{nullptr}};           // p11,p12,p21,p22 twins
+    Ctrl* d_ctrl = nullptr;
+    Ctrl* h_ctrl = nullptr;                 // pinned
+    double* d_partials = nullptr;
+    size_t partials_cap = 0;
+    // staging for the host-buffer entry point
+    uint8_t *d_f0 = nullptr, *d_f1 = nullptr;
+    float *d_uo = nullptr, *d_vo = nullptr;
+    size_t stage_pitch8 = 0;
+    int stage_w = 0, stage_h = 0;
+    cudaStream_t own_stream = nullptr;
+    std::vector<cudaEvent_t> events;
+    size_t ev_used = 0;
+    // sampler scratch (tvl1_sampler.cu)
+    void* samp = nullptr;
+};
+
+namespace tvl1 {
+
+int handle_device(const tvl1_handle* h) { return h->device; }
+void** handle_sampler_slot(tvl1_handle* h) { return &h->samp; }
+
+static int get_event(tvl1_handle* H, cudaEvent_t* out)
+{
+    if (H->ev_used == H->events.size()) {
+        cudaEvent_t e;
+        CK(cudaEventCreate(&e));
+        H->events.push_back(e);
+    }
+    *out = H->events[H->ev_used++];
+    return TVL1_OK;
+}
+
+static void release_arena(tvl1_handle* H)
+{
+    if (H->arena) cudaFree(H->arena);
+    H->arena = nullptr;
+    H->arena_bytes = 0;
+    H->cap_w = H->cap_h = 0;
+}
+
+static int ensure_capacity(tvl1_handle* H, int w, int h)
+{
+    if (H->arena && H->cap_w == w && H->cap_h == h && H->cap_scales == H->prm.nscales &&
+        H->cap_step == H->prm.scale_step)
+        return TVL1_OK;
+    release_arena(H);
+    int ws[TVL1_MAX_LEVELS + 1], hs[TVL1_MAX_LEVELS + 1];
+    const int L = pyramid_sizes(w, h, H->prm.nscales, H->prm.scale_step, ws, hs);
+    // carve: 256-byte aligned planes
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+    struct Plan { size_t I0, I1, u1, u2; } plan[TVL1_MAX_LEVELS];
+    for (int s = 0; s < L; s++) {
+        const int pitch = round_up(ws[s], 32);
+        const size_t b = (size_t)pitch * hs[s] * sizeof(float);
+        plan[s].I0 = carve(b); plan[s].I1 = carve(b); plan[s].u1 = carve(b); plan[s].u2 = carve(b);
+    }
+    const int pitch0 = round_up(w, 32);
+    const size_t b0 = (size_t)pitch0 * h * sizeof(float);
+    size_t o_scr[8], o_p[8];
+    for (int i = 0; i < 8; i++) o_scr[i] = carve(b0);   // I1x I1y I1wx I1wy grad rho u1x u2x
+    for (int i = 0; i < 8; i++) o_p[i] = carve(b0);
+    const size_t nb = iterate_max_blocks(w, h);
+    const size_t o_part = carve(nb * sizeof(double));
+    const size_t o_ctrl = carve(sizeof(Ctrl));
+    cudaError_t e = cudaMalloc(&H->arena, off);
+    if (e != cudaSuccess) {
+        H->arena = nullptr;
+        return fail(TVL1_ERR_NOMEM, "cudaMalloc(%zu bytes) for a %dx%d pair failed: %s", off, w, h,
+                    cudaGetErrorString(e));
+    }
+    H->arena_bytes = off;
+    for (int s = 0; s < L; s++) {
+        H->lv[s].w = ws[s]; H->lv[s].h = hs[s]; H->lv[s].pitch = round_up(ws[s], 32);
+        H->lv[s].I0 = (float*)(H->arena + plan[s].I0); H->lv[s].I1 = (float*)(H->arena + plan[s].I1);
+        H->lv[s].u1 = (float*)(H->arena + plan[s].u1); H->lv[s].u2 = (float*)(H->arena + plan[s].u2);
+    }
+    H->nlevels = L;
+    float** scr[8] = {&H->I1x, &H->I1y, &H->I1wx, &H->I1wy, &H->grad, &H->rho, &H->u1x, &H->u2x};
+    for (int i = 0; i < 8; i++) *scr[i] = (float*)(H->arena + o_scr[i]);
+    for (int i = 0; i < 8; i++) H->p[i / 2][i % 2] = (float*)(H->arena + o_p[i]);
+    H->d_partials = (double*)(H->arena + o_part);
+    H->partials_cap = nb;
+    H->d_ctrl = (Ctrl*)(H->arena + o_ctrl);
+    H->cap_w = w; H->cap_h = h; H->cap_scales = H->prm.nscales; H->cap_step = H->prm.scale_step;
+    // pad columns are read (never used) by the vectorised kernels: give them defined contents
+    CK(cudaMemset(H->arena, 0, off));
+    return TVL1_OK;
+}
+
+static int resolve_iterations(tvl1_handle* H)
+{
+    const tvl1_params& p = H->prm;
+    if (p.inner_iterations > 0 && p.outer_iterations > 0) {
+        H->inner = p.inner_iterations;
+        H->outer = p.outer_iterations;
+    } else {
+        // the cv::cuda API's flat `iterations` = inner 30 x outer ceil(N/30)
+        H->inner = p.inner_iterations > 0 ? p.inner_iterations : 30;
+        const int n = p.iterations > 0 ? p.iterations : 300;
+        H->outer = p.outer_iterations > 0 ? p.outer_iterations : (n + H->inner - 1) / H->inner;
+    }
+    return TVL1_OK;
+}
+
+static int check_params(const tvl1_params* p)
+{
+    if (!p) return fail(TVL1_ERR_INVALID, "params is null");
+    if (p->nscales <= 0) return fail(TVL1_ERR_INVALID, "nscales must be > 0");   // CV_Assert(nscales > 0)
+    if (p->nscales > TVL1_MAX_LEVELS) return fail(TVL1_ERR_INVALID, "nscales > %d", TVL1_MAX_LEVELS);
+    if (p->warps <= 0 || p->warps > TVL1_MAX_WARPS) return fail(TVL1_ERR_INVALID, "warps out of range");
+    if (!(p->scale_step > 0.0 && p->scale_step < 1.0)) return fail(TVL1_ERR_INVALID, "scaleStep must be in (0,1)");
+    if (p->scale_step == 0.5) return fail(TVL1_ERR_UNSUPPORTED, "scaleStep == 0.5 takes OpenCV's INTER_AREA path, not restated");
+    if (p->gamma != 0.0) return fail(TVL1_ERR_UNSUPPORTED, "gamma != 0 is not supported");
+    if (p->use_initial_flow) return fail(TVL1_ERR_UNSUPPORTED, "useInitialFlow is not supported (the reference never forwards it)");
+    if (p->median_filtering != 1 && p->median_filtering != 5)
+        return fail(TVL1_ERR_UNSUPPORTED, "medianFiltering must be 1 or 5");
+    if (!(p->theta > 0.0)) return fail(TVL1_ERR_INVALID, "theta must be > 0");
+    return TVL1_OK;
+}
+
+// the solve proper; everything is enqueued on `st`
+static int calc_device(tvl1_handle* H, const uint8_t* f0, size_t pitch0, const uint8_t* f1, size_t pitch1,
+                       int w, int h, float* d_u, float* d_v, size_t pitch_out, cudaStream_t st,
+                       tvl1_stats* stats)
+{
+    if (!f0 || !f1 || !d_u || !d_v) return fail(TVL1_ERR_INVALID, "null image or flow pointer");
+    if (w <= 0 || h <= 0) return fail(TVL1_ERR_INVALID, "empty image (%dx%d)", w, h);
+    if (w > 32767 || h > 32767) return fail(TVL1_ERR_INVALID, "image side > 32767 (remap uses int16 coordinates)");
+    if (pitch0 < (size_t)w || pitch1 < (size_t)w || pitch_out < (size_t)w * 4)
+        return fail(TVL1_ERR_INVALID, "pitch smaller than a row");
+    CK(cudaSetDevice(H->device));
+    int rc;
+    if ((rc = ensure_capacity(H, w, h))) return rc;
+    if ((rc = upload_cubic_table(H->device))) return rc;
+    const tvl1_params& P = H->prm;
+    const int L = H->nlevels, W = P.warps;
+    const float l_t = (float)(P.lambda * P.theta);
+    const float taut = (float)(P.tau / P.theta);
+    const float theta = (float)P.theta;
+    long long launches = 0;
+    H->ev_used = 0;
+
+    cudaEvent_t ev_begin, ev_pyr, ev_end;
+    if ((rc = get_event(H, &ev_begin)) || (rc = get_event(H, &ev_pyr)) || (rc = get_event(H, &ev_end))) return rc;
+    struct Span { cudaEvent_t a, b; int kind, level; };
+    std::vector<Span> spans;
+    auto span_begin = [&](int kind, int level) -> int {
+        Span s; s.kind = kind; s.level = level;
+        int r = get_event(H, &s.a); if (r) return r;
+        r = get_event(H, &s.b); if (r) return r;
+        cudaEventRecord(s.a, st);
+        spans.push_back(s);
+        return TVL1_OK;
+    };
+    auto span_end = [&]() { cudaEventRecord(spans.back().b, st); };
+
+    CK(cudaEventRecord(ev_begin, st));
+    CK(cudaMemsetAsync(H->d_ctrl, 0, sizeof(Ctrl), st));
+    // (1) pyramid: convert, then resize level by level
+    if ((rc = launch_convert(f0, pitch0, w, h, H->lv[0].I0, H->lv[0].pitch, st))) return rc;
+    if ((rc = launch_convert(f1, pitch1, w, h, H->lv[0].I1, H->lv[0].pitch, st))) return rc;
+    launches += 2;
+    for (int s = 1; s < L; s++) {
+        const Level &a = H->lv[s - 1], &b = H->lv[s];
+        if ((rc = launch_resize(a.I0, a.w, a.h, a.pitch, b.I0, b.w, b.h, b.pitch, P.scale_step, 1.f, 0, st))) return rc;
+        if ((rc = launch_resize(a.I1, a.w, a.h, a.pitch, b.I1, b.w, b.h, b.pitch, P.scale_step, 1.f, 0, st))) return rc;
+        launches += 2;
+    }
+    {
+        const Level& c = H->lv[L - 1];
+        const size_t b = (size_t)c.pitch * c.h * sizeof(float);
+        CK(cudaMemsetAsync(c.u1, 0, b, st));
+        CK(cudaMemsetAsync(c.u2, 0, b, st));
+    }
+    CK(cudaEventRecord(ev_pyr, st));
+
+    const size_t hdr = offsetof(Ctrl, iters);
+    for (int s = L - 1; s >= 0; --s) {
+        const Level& lv = H->lv[s];
+        const size_t pb = (size_t)lv.pitch * lv.h * sizeof(float);
+        const float scaled_eps = (float)(P.epsilon * P.epsilon * (double)(lv.w * lv.h));
+        if ((rc = span_begin(3, s))) return rc;
+        if ((rc = launch_gradient(lv.I1, lv.w, lv.h, lv.pitch, H->I1x, H->I1y, st))) return rc;
+        launches++;
+        for (int k = 0; k < 4; k++) CK(cudaMemsetAsync(H->p[k][0], 0, pb, st));
+        span_end();
+
+        IterArgs ia;
+        ia.I1wx = H->I1wx; ia.I1wy = H->I1wy; ia.grad = H->grad; ia.rho_c = H->rho;
+        ia.u1[0] = lv.u1; ia.u1[1] = H->u1x; ia.u2[0] = lv.u2; ia.u2[1] = H->u2x;
+        for (int k = 0; k < 2; k++) { ia.p11[k] = H->p[0][k]; ia.p12[k] = H->p[1][k]; ia.p21[k] = H->p[2][k]; ia.p22[k] = H->p[3][k]; }
+        ia.w = lv.w; ia.h = lv.h; ia.pitch = lv.pitch;
+        ia.l_t = l_t; ia.theta = theta; ia.taut = taut; ia.scaled_eps = scaled_eps;
+        ia.level = s; ia.ctrl = H->d_ctrl; ia.partials = H->d_partials; ia.errlog = nullptr;
+        MedianArgs ma;
+        ma.u1[0] = lv.u1; ma.u1[1] = H->u1x; ma.u2[0] = lv.u2; ma.u2[1] = H->u2x;
+        ma.w = lv.w; ma.h = lv.h; ma.pitch = lv.pitch; ma.level = s; ma.ctrl = H->d_ctrl;
+        WarpArgs wa;
+        wa.I0 = lv.I0; wa.I1 = lv.I1; wa.I1x = H->I1x; wa.I1y = H->I1y;
+        wa.u1[0] = lv.u1; wa.u1[1] = H->u1x; wa.u2[0] = lv.u2; wa.u2[1] = H->u2x;
+        wa.I1wx = H->I1wx; wa.I1wy = H->I1wy; wa.grad = H->grad; wa.rho_c = H->rho;
+        wa.w = lv.w; wa.h = lv.h; wa.pitch = lv.pitch; wa.level = s; wa.ctrl = H->d_ctrl;
+
+        for (int wi = 0; wi < W; ++wi) {
+            const int slot = s * W + wi;
+            ia.slot = slot;
+            ma.slot = slot;
+            // (2) warp I1 by the current flow; also re-arms the stop test (error = FLT_MAX)
+            if ((rc = span_begin(1, s))) return rc;
+            if ((rc = launch_warp(wa, st))) return rc;
+            launches++;
+            span_end();
+            // (3) outer iterations: median + `inner` primal-dual iterations, each kernel a
+            // no-op once the device-side stop flag is set; one host read-back per outer
+            // iteration decides whether another is needed.
+            for (int no = 0; no < H->outer; ++no) {
+                if (P.median_filtering > 1) {
+                    if ((rc = span_begin(2, s))) return rc;
+                    if ((rc = launch_median(ma, 2, st))) return rc;
+                    launches++;
+                    span_end();
+                }
+                if ((rc = span_begin(0, s))) return rc;
+                for (int ni = 0; ni < H->inner; ++ni) {
+                    if ((rc = launch_iterate(ia, st))) return rc;
+                }
+                launches += H->inner;
+                span_end();
+                CK(cudaMemcpyAsync(H->h_ctrl, H->d_ctrl, hdr, cudaMemcpyDeviceToHost, st));
+                CK(cudaStreamSynchronize(st));
+                if (H->h_ctrl->done) break;
+            }
+        }
+        if (s == 0) break;
+        // flow upsample to the next finer level (A.2): resize to its size, times 1/scaleStep
+        const Level& up = H->lv[s - 1];
+        const int uc = H->h_ctrl->ucur[s];
+        const float mul = (float)(1 / P.scale_step);
+        if ((rc = span_begin(3, s))) return rc;
+        if ((rc = launch_resize(uc ? H->u1x : lv.u1, lv.w, lv.h, lv.pitch, up.u1, up.w, up.h, up.pitch, 0.0, mul, 1, st))) return rc;
+        if ((rc = launch_resize(uc ? H->u2x : lv.u2, lv.w, lv.h, lv.pitch, up.u2, up.w, up.h, up.pitch, 0.0, mul, 1, st))) return rc;
+        launches += 2;
+        span_end();
+    }
+    // A.8: planar output
+    {
+        const int uc = H->h_ctrl->ucur[0];
+        const Level& l0 = H->lv[0];
+        CK(cudaMemcpy2DAsync(d_u, pitch_out, uc ? H->u1x : l0.u1, (size_t)l0.pitch * 4, (size_t)w * 4, h, cudaMemcpyDeviceToDevice, st));
+        CK(cudaMemcpy2DAsync(d_v, pitch_out, uc ? H->u2x : l0.u2, (size_t)l0.pitch * 4, (size_t)w * 4, h, cudaMemcpyDeviceToDevice, st));
+    }
+    CK(cudaEventRecord(ev_end, st));
+    CK(cudaMemcpyAsync(H->h_ctrl, H->d_ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+
+    if (stats) {
+        memset(stats, 0, sizeof(*stats));
+        stats->levels = L;
+        stats->warps = W;
+        double bytes = 70.0 * (double)w * h;
+        for (int s = 0; s < L; s++) {
+            stats->width[s] = H->lv[s].w;
+            stats->height[s] = H->lv[s].h;
+            const double px = (double)H->lv[s].w * H->lv[s].h;
+            double per_px = 12.0;
+            for (int wi = 0; wi < W; wi++) {
+                const int n = H->h_ctrl->iters[s * W + wi], o = H->h_ctrl->outer[s * W + wi];
+                stats->iters[s * W + wi] = n;
+                stats->outer[s * W + wi] = o;
+                stats->total_iterations += n;
+                stats->px_iterations += (long long)px * n;
+                per_px += 40.0 + 64.0 * n + 16.0 * o;
+            }
+            bytes += px * per_px;
+        }
+        stats->algorithmic_bytes = bytes;
+        stats->launches = launches;
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ev_begin, ev_end);
+        stats->ms_total = ms;
+        cudaEventElapsedTime(&ms, ev_begin, ev_pyr);
+        stats->ms_pyramid = ms;
+        for (const Span& sp : spans) {
+            cudaEventElapsedTime(&ms, sp.a, sp.b);
+            switch (sp.kind) {
+                case 0: stats->ms_iterate += ms; stats->ms_iterate_level[sp.level] += ms; break;
+                case 1: stats->ms_warp += ms; break;
+                case 2: stats->ms_median += ms; break;
+                default: stats->ms_other += ms; break;
+            }
+        }
+    }
+    return TVL1_OK;
+}
+
+}  // namespace tvl1
+
+// =================================================================== C ABI
+
+extern "C" {
+
+const char* tvl1_version(void) { return "fibsem-optflow_b200 0.1 (sm_100a)"; }
+const char* tvl1_last_error(void) { return tvl1::g_err; }
+
+void tvl1_default_params(tvl1_params* p)
+{
+    if (!p) return;
+    memset(p, 0, sizeof(*p));
+    // generate_TV_args defaults, reference src/optflow.cpp:503-512
+    p->tau = 0.25; p->lambda = 0.05; p->theta = 0.3; p->nscales = 10; p->warps = 5;
+    p->epsilon = 0.01; p->iterations = 300; p->scale_step = 0.8; p->gamma = 0.0;
+    p->use_initial_flow = 0;
+    p->inner_iterations = 0; p->outer_iterations = 0;   // derived from iterations
+    p->median_filtering = 5;                             // CPU-class semantics
+}
+
+int tvl1_create(const tvl1_params* p, int device, tvl1_handle** out)
+{
+    if (!out) return fail(TVL1_ERR_INVALID, "out is null");
+    *out = nullptr;
+    int rc = check_params(p);
+    if (rc) return rc;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0)
+        return fail(TVL1_ERR_CUDA, "no CUDA device (%s); this library has no CPU path",
+                    e == cudaSuccess ? "count = 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= n) return fail(TVL1_ERR_INVALID, "device %d out of range (%d devices)", device, n);
+    CK(cudaSetDevice(device));
+    tvl1_handle* H = new tvl1_handle();
+    H->device = device;
+    H->prm = *p;
+    resolve_iterations(H);
+    e = cudaMallocHost(&H->h_ctrl, sizeof(Ctrl));
+    if (e != cudaSuccess) { delete H; return fail(TVL1_ERR_CUDA, "cudaMallocHost: %s", cudaGetErrorString(e)); }
+    memset(H->h_ctrl, 0, sizeof(Ctrl));
+    e = cudaStreamCreateWithFlags(&H->own_stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { cudaFreeHost(H->h_ctrl); delete H; return fail(TVL1_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
+    rc = upload_cubic_table(device);
+    if (rc) { tvl1_destroy(H); return rc; }
+    *out = H;
+    return TVL1_OK;
+}
+
+void tvl1_destroy(tvl1_handle* H)
+{
+    if (!H) return;
+    cudaSetDevice(H->device);
+    tvl1::release_arena(H);
+    if (H->h_ctrl) cudaFreeHost(H->h_ctrl);
+    if (H->d_f0) cudaFree(H->d_f0);
+    if (H->d_f1) cudaFree(H->d_f1);
+    if (H->d_uo) cudaFree(H->d_uo);
+    if (H->d_vo) cudaFree(H->d_vo);
+    tvl1::sampler_release(H->samp);
+    for (cudaEvent_t e : H->events) cudaEventDestroy(e);
+    if (H->own_stream) cudaStreamDestroy(H->own_stream);
+    delete H;
+}
+
+int tvl1_set_params(tvl1_handle* H, const tvl1_params* p)
+{
+    if (!H) return fail(TVL1_ERR_INVALID, "handle is null");
+    int rc = check_params(p);
+    if (rc) return rc;
+    H->prm = *p;
+    return resolve_iterations(H);
+}
+
+int tvl1_set_timing(tvl1_handle* H, int enabled)
+{
+    if (!H) return fail(TVL1_ERR_INVALID, "handle is null");
+    H->timing = enabled != 0;
+    return TVL1_OK;
+}
+
+int tvl1_calc_u8(tvl1_handle* H, const uint8_t* d_frame0, size_t pitch0, const uint8_t* d_frame1, size_t pitch1,
+                 int width, int height, float* d_u, float* d_v, size_t pitch_out, void* stream, tvl1_stats* stats)
+{
+    if (!H) return fail(TVL1_ERR_INVALID, "handle is null");
+    return calc_device(H, d_frame0, pitch0, d_frame1, pitch1, width, height, d_u, d_v, pitch_out,
+                       (cudaStream_t)stream, stats);
+}
+
+int tvl1_calc_u8_host(tvl1_handle* H, const uint8_t* h_frame0, size_t pitch0, const uint8_t* h_frame1, size_t pitch1,
+                      int width, int height, float* h_u, float* h_v, size_t pitch_out, tvl1_stats* stats)
+{
+    if (!H) return fail(TVL1_ERR_INVALID, "handle is null");
+    if (!h_frame0 || !h_frame1 || !h_u || !h_v) return fail(TVL1_ERR_INVALID, "null image or flow pointer");
+    if (width <= 0 || height <= 0) return fail(TVL1_ERR_INVALID, "empty image (%dx%d)", width, height);
+    if (pitch0 < (size_t)width || pitch1 < (size_t)width || pitch_out < (size_t)width * 4)
+        return fail(TVL1_ERR_INVALID, "pitch smaller than a row");
+    CK(cudaSetDevice(H->device));
+    if (H->stage_w != width || H->stage_h != height) {
+        if (H->d_f0) cudaFree(H->d_f0);
+        if (H->d_f1) cudaFree(H->d_f1);
+        if (H->d_uo) cudaFree(H->d_uo);
+        if (H->d_vo) cudaFree(H->d_vo);
+        H->d_f0 = H->d_f1 = nullptr; H->d_uo = H->d_vo = nullptr; H->stage_w = H->stage_h = 0;
+        H->stage_pitch8 = (size_t)round_up(width, 128);
+        CK(cudaMalloc(&H->d_f0, H->stage_pitch8 * height));
+        CK(cudaMalloc(&H->d_f1, H->stage_pitch8 * height));
+        CK(cudaMalloc(&H->d_uo, (size_t)width * height * 4));
+        CK(cudaMalloc(&H->d_vo, (size_t)width * height * 4));
+        H->stage_w = width; H->stage_h = height;
+    }
+    cudaStream_t st = H->own_stream;
+    CK(cudaMemcpy2DAsync(H->d_f0, H->stage_pitch8, h_frame0, pitch0, width, height, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpy2DAsync(H->d_f1, H->stage_pitch8, h_frame1, pitch1, width, height, cudaMemcpyHostToDevice, st));
+    int rc = calc_device(H, H->d_f0, H->stage_pitch8, H->d_f1, H->stage_pitch8, width, height, H->d_uo, H->d_vo,
+                         (size_t)width * 4, st, stats);
+    if (rc) return rc;
+    CK(cudaMemcpy2DAsync(h_u, pitch_out, H->d_uo, (size_t)width * 4, (size_t)width * 4, height, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpy2DAsync(h_v, pitch_out, H->d_vo, (size_t)width * 4, (size_t)width * 4, height, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return TVL1_OK;
+}
+
+int tvl1_mask_flow_u8(tvl1_handle* H, const uint8_t* d_frame1, size_t pitch1, int width, int height,
+                      float* d_u, float* d_v, size_t pitch_out, void* stream)
+{
+    if (!H) return fail(TVL1_ERR_INVALID, "handle is null");
+    if (!d_frame1 || !d_u || !d_v || width <= 0 || height <= 0) return fail(TVL1_ERR_INVALID, "bad argument");
+    CK(cudaSetDevice(H->device));
+    dim3 b(32, 8);
+    k_mask_flow<<<grid2d(width, height, b), b, 0, (cudaStream_t)stream>>>(d_frame1, pitch1, width, height, d_u, d_v, pitch_out / 4);
+    CK(cudaGetLastError());
+    return TVL1_OK;
+}
+
+// ---- stage-level entry points
+
+int tvl1_k_convert_u8(const uint8_t* d_src, size_t pitch_bytes, int w, int h, float* d_dst, int pitch, void* stream)
+{
+    if (!d_src || !d_dst || w <= 0 || h <= 0 || pitch % 4) return fail(TVL1_ERR_INVALID, "bad argument");
+    return launch_convert(d_src, pitch_bytes, w, h, d_dst, pitch, (cudaStream_t)stream);
+}
+
+int tvl1_k_resize(const float* d_src, int sw, int sh, int spitch, float* d_dst, int dw, int dh, int dpitch,
+                  double inv_scale, float mul, void* stream)
+{
+    if (!d_src || !d_dst || sw <= 0 || sh <= 0 || dw <= 0 || dh <= 0) return fail(TVL1_ERR_INVALID, "bad argument");
+    return launch_resize(d_src, sw, sh, spitch, d_dst, dw, dh, dpitch, inv_scale, mul, mul != 1.f, (cudaStream_t)stream);
+}
+
+int tvl1_k_centered_gradient(const float* d_src, int w, int h, int pitch, float* d_dx, float* d_dy, void* stream)
+{
+    if (!d_src || !d_dx || !d_dy || w <= 0 || h <= 0) return fail(TVL1_ERR_INVALID, "bad argument");
+    return launch_gradient(d_src, w, h, pitch, d_dx, d_dy, (cudaStream_t)stream);
+}
+
+int tvl1_k_warp(const float* d_I0, const float* d_I1, const float* d_I1x, const float* d_I1y, const float* d_u1,
+                const float* d_u2, int w, int h, int pitch, float* d_I1wx, float* d_I1wy, float* d_grad,
+                float* d_rho_c, void* stream)
+{
+    if (!d_I0 || !d_I1 || !d_I1x || !d_I1y || !d_u1 || !d_u2 || !d_I1wx || !d_I1wy || !d_grad || !d_rho_c ||
+        w <= 0 || h <= 0)
+        return fail(TVL1_ERR_INVALID, "bad argument");
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    int rc = upload_cubic_table(dev);
+    if (rc) return rc;
+    WarpArgs a;
+    a.I0 = d_I0; a.I1 = d_I1; a.I1x = d_I1x; a.I1y = d_I1y;
+    a.u1[0] = a.u1[1] = d_u1; a.u2[0] = a.u2[1] = d_u2;
+    a.I1wx = d_I1wx; a.I1wy = d_I1wy; a.grad = d_grad; a.rho_c = d_rho_c;
+    a.w = w; a.h = h; a.pitch = pitch; a.level = -1; a.ctrl = nullptr;
+    return launch_warp(a, (cudaStream_t)stream);
+}
+
+int tvl1_k_iterate(const float* d_I1wx, const float* d_I1wy, const float* d_grad, const float* d_rho_c,
+                   float* d_u1, float* d_u2, float* d_p11, float* d_p12, float* d_p21, float* d_p22,
+                   int w, int h, int pitch, float l_t, float theta, float taut, int n, double* errors, void* stream)
+{
+    if (!d_I1wx || !d_I1wy || !d_grad || !d_rho_c || !d_u1 || !d_u2 || !d_p11 || !d_p12 || !d_p21 || !d_p22 ||
+        w <= 0 || h <= 0 || pitch % 4 || pitch < w || n < 0)
+        return fail(TVL1_ERR_INVALID, "bad argument");
+    if (n > TVL1_MAX_LEVELS * TVL1_MAX_WARPS) return fail(TVL1_ERR_INVALID, "n too large");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t pb = (size_t)pitch * h * sizeof(float);
+    const size_t nb = iterate_max_blocks(w, h);
+    char* tmp = nullptr;
+    const size_t ctrl_off = 6 * pb, part_off = ctrl_off + 1024 * ((sizeof(Ctrl) + 1023) / 1024);
+    const size_t log_off = part_off + nb * sizeof(double);
+    const size_t total = log_off + (size_t)(n + 1) * sizeof(double);
+    CK(cudaMalloc(&tmp, total));
+    cudaError_t e = cudaMemsetAsync(tmp, 0, total, st);
+    if (e != cudaSuccess) { cudaFree(tmp); return fail(TVL1_ERR_CUDA, "memset: %s", cudaGetErrorString(e)); }
+    float* tw[6];
+    for (int k = 0; k < 6; k++) tw[k] = (float*)(tmp + k * pb);
+    IterArgs a;
+    a.I1wx = d_I1wx; a.I1wy = d_I1wy; a.grad = d_grad; a.rho_c = d_rho_c;
+    a.u1[0] = d_u1; a.u1[1] = tw[0]; a.u2[0] = d_u2; a.u2[1] = tw[1];
+    a.p11[0] = d_p11; a.p11[1] = tw[2]; a.p12[0] = d_p12; a.p12[1] = tw[3];
+    a.p21[0] = d_p21; a.p21[1] = tw[4]; a.p22[0] = d_p22; a.p22[1] = tw[5];
+    a.w = w; a.h = h; a.pitch = pitch; a.l_t = l_t; a.theta = theta; a.taut = taut;
+    a.scaled_eps = -1.f;   // never stops
+    a.level = 0; a.slot = 0;
+    a.ctrl = (Ctrl*)(tmp + ctrl_off);
+    a.partials = (double*)(tmp + part_off);
+    a.errlog = (double*)(tmp + log_off);
+    int rc = TVL1_OK;
+    for (int i = 0; i < n && !rc; i++) rc = launch_iterate(a, st);
+    if (!rc && (n & 1)) {
+        float* dst[6] = {d_u1, d_u2, d_p11, d_p12, d_p21, d_p22};
+        for (int k = 0; k < 6 && !rc; k++)
+            if (cudaMemcpyAsync(dst[k], tw[k], pb, cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+                rc = fail(TVL1_ERR_CUDA, "copy back failed");
+    }
+    if (!rc && errors && n > 0 &&
+        cudaMemcpyAsync(errors, tmp + log_off, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st) != cudaSuccess)
+        rc = fail(TVL1_ERR_CUDA, "error log copy failed");
+    e = cudaStreamSynchronize(st);
+    if (!rc && e != cudaSuccess) rc = fail(TVL1_ERR_CUDA, "iterate: %s", cudaGetErrorString(e));
+    cudaFree(tmp);
+    return rc;
+}
+
+int tvl1_k_median5(const float* d_src, int w, int h, int pitch, float* d_dst, void* stream)
+{
+    if (!d_src || !d_dst || d_src == d_dst || w <= 0 || h <= 0) return fail(TVL1_ERR_INVALID, "bad argument");
+    MedianArgs a;
+    a.u1[0] = const_cast<float*>(d_src); a.u1[1] = d_dst; a.u2[0] = a.u2[1] = nullptr;
+    a.w = w; a.h = h; a.pitch = pitch; a.level = -1; a.slot = 0; a.ctrl = nullptr;
+    return launch_median(a, 1, (cudaStream_t)stream);
+}
+
+int tvl1_pyramid_sizes(int w, int h, int nscales, double scale_step, int* ws, int* hs)
+{
+    if (!ws || !hs || w <= 0 || h <= 0 || nscales <= 0) return fail(TVL1_ERR_INVALID, "bad argument");
+    return pyramid_sizes(w, h, nscales, scale_step, ws, hs);
+}
+
+// ---- device-memory helpers
+
+int tvl1_dev_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int tvl1_dev_alloc(int device, size_t bytes, void** out)
+{
+    if (!out) return fail(TVL1_ERR_INVALID, "out is null");
+    CK(cudaSetDevice(device));
+    CK(cudaMalloc(out, bytes ? bytes : 1));
+    return TVL1_OK;
+}
+
+int tvl1_dev_free(int device, void* p)
+{
+    CK(cudaSetDevice(device));
+    CK(cudaFree(p));
+    return TVL1_OK;
+}
+
+int tvl1_dev_memset(void* d, int v, size_t bytes) { CK(cudaMemset(d, v, bytes)); return TVL1_OK; }
+int tvl1_dev_h2d(void* d, const void* h, size_t bytes) { CK(cudaMemcpy(d, h, bytes, cudaMemcpyHostToDevice)); return TVL1_OK; }
+int tvl1_dev_d2h(void* h, const void* d, size_t bytes) { CK(cudaMemcpy(h, d, bytes, cudaMemcpyDeviceToHost)); return TVL1_OK; }
+int tvl1_dev_sync(int device) { CK(cudaSetDevice(device)); CK(cudaDeviceSynchronize()); return TVL1_OK; }
+int tvl1_host_alloc_pinned(size_t bytes, void** out)
+{
+    if (!out) return fail(TVL1_ERR_INVALID, "out is null");
+    CK(cudaMallocHost(out, bytes ? bytes : 1));
+    return TVL1_OK;
+}
+int tvl1_host_free_pinned(void* p) { CK(cudaFreeHost(p)); return TVL1_OK; }
+
+}  // extern "C"

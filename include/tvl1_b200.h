@@ -1,0 +1,173 @@
+/*
+ * tvl1_b200.h -- C ABI of the B200-native TV-L1 flow stage.
+ *
+ * Drop-in boundary for fibsem-optflow's flow stage.  The reference has no FFI of
+ * its own; the seam is two C++ functions, and every entry point below names the
+ * reference interface it replaces (paths relative to the reference repo):
+ *
+ *   tvl1_default_params / tvl1_params   <- generate_TV_args   src/optflow.cpp:500-514
+ *   tvl1_create / tvl1_destroy          <- OpticalFlowDual_TVL1::create, called per
+ *                                          solve in TVL1_solve   src/optflow.cpp:518
+ *   tvl1_calc_u8 / tvl1_calc_u8_host    <- TVL1_solve (solver->calc)
+ *                                          src/optflow.h:31, src/optflow.cpp:516-520
+ *   tvl1_mask_flow_u8                   <- threshold + setTo in solve_wrapper
+ *                                          src/optflow.cpp:471-473
+ *   tvl1_sample_matches[_host]          <- mask build src/optflow.cpp:488-493 and
+ *                                          random_points src/optflow.h:33,
+ *                                          src/optflow.cpp:522-572
+ *
+ * Conventions: plain pointers and sizes, no C++ or torch types.  "d_" pointers are
+ * device memory on the handle's device, "h_" pointers are host memory.  8-bit images
+ * are single channel rows with a byte pitch (the reference passes GpuMat ROI views,
+ * src/optflow.cpp:362,382).  Flow is returned PLANAR (u then v), fp32, with a byte
+ * pitch -- the reference splits OpenCV's interleaved result immediately
+ * (src/optflow.cpp:404).  All functions return TVL1_OK (0) or a negative status and
+ * never throw; tvl1_last_error() describes the last failure on the calling thread.
+ * A handle is bound to one device and must be used by one host thread at a time.
+ */
+#ifndef TVL1_B200_H
+#define TVL1_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TVL1_OK 0
+#define TVL1_ERR_INVALID (-1)   /* bad argument */
+#define TVL1_ERR_CUDA (-2)      /* CUDA runtime error, see tvl1_last_error() */
+#define TVL1_ERR_UNSUPPORTED (-3)
+#define TVL1_ERR_NOMEM (-4)
+
+#define TVL1_MAX_LEVELS 32
+#define TVL1_MAX_WARPS 64
+
+typedef struct tvl1_handle tvl1_handle;
+
+/* The ten keys of generate_TV_args (src/optflow.cpp:503-512) plus the CPU-class
+ * parameters OpenCV's DualTVL1 has and the cv::cuda API lacks. */
+typedef struct tvl1_params {
+    double tau;             /* 0.25 */
+    double lambda;          /* reference wrapper default 0.05 (OpenCV 0.15) */
+    double theta;           /* 0.3 */
+    double epsilon;         /* 0.01 */
+    double scale_step;      /* "scaleStep", 0.8 */
+    double gamma;           /* 0; only 0 is supported */
+    int nscales;            /* reference wrapper default 10 (OpenCV 5) */
+    int warps;              /* 5 */
+    int iterations;         /* 300; used when inner/outer are <= 0:
+                               inner = 30, outer = ceil(iterations / 30) */
+    int inner_iterations;   /* <= 0: derive from iterations */
+    int outer_iterations;   /* <= 0: derive from iterations */
+    int median_filtering;   /* 5 (CPU class); 1 = off */
+    int use_initial_flow;   /* read by the reference but never forwarded
+                               (src/optflow.cpp:512,518); must be 0 */
+    int reserved[3];
+} tvl1_params;
+
+/* Iteration counts and stage times of the last calc. */
+typedef struct tvl1_stats {
+    int levels;                                     /* pyramid levels actually used */
+    int warps;
+    int width[TVL1_MAX_LEVELS], height[TVL1_MAX_LEVELS];
+    int iters[TVL1_MAX_LEVELS * TVL1_MAX_WARPS];    /* [level * warps + warp], level 0 = finest */
+    int outer[TVL1_MAX_LEVELS * TVL1_MAX_WARPS];    /* outer iterations (median passes) run */
+    long long total_iterations;
+    long long px_iterations;                        /* sum over (level,warp) of px * iters */
+    double algorithmic_bytes;                       /* BASELINE.md section 4 byte model */
+    float ms_total, ms_pyramid, ms_warp, ms_iterate, ms_median, ms_other;  /* CUDA events on
+                                                       the solve's stream */
+    float ms_iterate_level[TVL1_MAX_LEVELS];        /* ms_iterate split by level */
+    long long launches;                             /* kernels launched by the last calc */
+} tvl1_stats;
+
+const char* tvl1_version(void);
+const char* tvl1_last_error(void);
+
+/* Reference-wrapper defaults of generate_TV_args (src/optflow.cpp:503-512). */
+void tvl1_default_params(tvl1_params* p);
+
+int tvl1_create(const tvl1_params* p, int device, tvl1_handle** out);
+void tvl1_destroy(tvl1_handle* h);
+int tvl1_set_params(tvl1_handle* h, const tvl1_params* p);
+/* per-stage CUDA-event timing in tvl1_stats (adds stream syncs); default off */
+int tvl1_set_timing(tvl1_handle* h, int enabled);
+
+/* Flow from frame0 to frame1 (device pointers).  stream is a cudaStream_t (may be 0).
+ * Returns after the result is complete on `stream` and the stop test has been resolved
+ * (the call synchronises the stream: the iteration count is data dependent). */
+int tvl1_calc_u8(tvl1_handle* h, const uint8_t* d_frame0, size_t pitch0,
+                 const uint8_t* d_frame1, size_t pitch1, int width, int height,
+                 float* d_u, float* d_v, size_t pitch_out, void* stream, tvl1_stats* stats);
+
+/* Same with host buffers: H2D of both frames, solve, D2H of both planes. */
+int tvl1_calc_u8_host(tvl1_handle* h, const uint8_t* h_frame0, size_t pitch0,
+                      const uint8_t* h_frame1, size_t pitch1, int width, int height,
+                      float* h_u, float* h_v, size_t pitch_out, tvl1_stats* stats);
+
+/* flow = 0 where frame1 <= 1 (src/optflow.cpp:471-473). */
+int tvl1_mask_flow_u8(tvl1_handle* h, const uint8_t* d_frame1, size_t pitch1, int width,
+                      int height, float* d_u, float* d_v, size_t pitch_out, void* stream);
+
+/* random_points (features == false path).  mask = (frame0 > 1) | (frame1 > 1); the mask's
+ * non-zero pixels in row-major order are shuffled exactly as libstdc++'s
+ * std::random_shuffle driven by glibc rand() does: seed < 0 reproduces the reference's
+ * debug mode (no srand), seed >= 0 reproduces srand(seed) (the reference uses time(0)).
+ * The first min(npoints, count) entries are returned:
+ *   p = (pos + roi0) * inv_scale,  q = (pos + roi1 + flow(pos)) * inv_scale   in fp32,
+ * widened to double as jsoncpp stores them; w = 1.  An empty mask yields the single dummy
+ * entry (-1,-1,-1,-1, w = 0).  out arrays are HOST memory with room for max(npoints,1)
+ * entries; positions (may be NULL) receives npoints (x,y) int pairs.  *n_out = entries. */
+int tvl1_sample_matches(tvl1_handle* h, const uint8_t* d_frame0, size_t pitch0,
+                        const uint8_t* d_frame1, size_t pitch1,
+                        const float* d_u, const float* d_v, size_t pitch_flow,
+                        int width, int height, int roi0_x, int roi0_y, int roi1_x, int roi1_y,
+                        float scale, int npoints, long long seed,
+                        double* px, double* py, double* qx, double* qy, double* w,
+                        int* positions, int* n_out, void* stream);
+
+/* ---- stage-level entry points: the individual kernels, exposed so that each can be
+ * checked against the oracle on its own (tests/) and profiled on its own (bench.py).
+ * Planes are fp32 with a pitch in ELEMENTS; pointers are device memory. ---- */
+int tvl1_k_convert_u8(const uint8_t* d_src, size_t pitch_bytes, int w, int h, float* d_dst,
+                      int pitch, void* stream);
+int tvl1_k_resize(const float* d_src, int sw, int sh, int spitch, float* d_dst, int dw, int dh,
+                  int dpitch, double inv_scale /* <= 0: explicit size */, float mul, void* stream);
+int tvl1_k_centered_gradient(const float* d_src, int w, int h, int pitch, float* d_dx,
+                             float* d_dy, void* stream);
+int tvl1_k_warp(const float* d_I0, const float* d_I1, const float* d_I1x, const float* d_I1y,
+                const float* d_u1, const float* d_u2, int w, int h, int pitch,
+                float* d_I1wx, float* d_I1wy, float* d_grad, float* d_rho_c, void* stream);
+/* n inner iterations with no stop test; state planes are updated in place (the result
+ * is copied back if it ends in the internal twin buffers).  errors (host, may be NULL)
+ * receives the n per-iteration error sums. */
+int tvl1_k_iterate(const float* d_I1wx, const float* d_I1wy, const float* d_grad,
+                   const float* d_rho_c, float* d_u1, float* d_u2, float* d_p11, float* d_p12,
+                   float* d_p21, float* d_p22, int w, int h, int pitch,
+                   float l_t, float theta, float taut, int n, double* errors, void* stream);
+int tvl1_k_median5(const float* d_src, int w, int h, int pitch, float* d_dst, void* stream);
+
+/* pyramid level sizes for (w, h): returns levels used (A.2 stop rule) */
+int tvl1_pyramid_sizes(int w, int h, int nscales, double scale_step, int* ws, int* hs);
+
+/* glibc-compatible rand() stream used by the sampler: fills out[0..n) with the values
+ * rand() returns at calls skip .. skip+n-1 after srand(seed) (seed < 0: unseeded). */
+int tvl1_glibc_rand(long long seed, long long skip, int n, int* out);
+
+/* minimal device-memory helpers so that C / ctypes callers need no other CUDA binding */
+int tvl1_dev_count(void);
+int tvl1_dev_alloc(int device, size_t bytes, void** out);
+int tvl1_dev_free(int device, void* p);
+int tvl1_dev_memset(void* d_dst, int value, size_t bytes);
+int tvl1_dev_h2d(void* d_dst, const void* h_src, size_t bytes);
+int tvl1_dev_d2h(void* h_dst, const void* d_src, size_t bytes);
+int tvl1_dev_sync(int device);
+int tvl1_host_alloc_pinned(size_t bytes, void** out);
+int tvl1_host_free_pinned(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TVL1_B200_H */

@@ -1,0 +1,92 @@
+"""Stage-level parity: each CUDA kernel, called through the C ABI, against the C oracle on
+the same seeded inputs.  Bar: bit-exact (all stages are fp32 with one rounding per op)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+SIZES = [(16, 16), (37, 53), (64, 124), (65, 125), (97, 249), (130, 500), (240, 1000)]
+
+
+def rnd(rng, h, w, scale=1.0):
+    return (rng.standard_normal((h, w)) * scale).astype(np.float32)
+
+
+def test_convert_u8(gpu, orc):
+    rng = np.random.default_rng(0)
+    for h, w in SIZES:
+        img = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        assert np.array_equal(gpu.k_convert_u8(img), img.astype(np.float32))
+
+
+@pytest.mark.parametrize("h,w", SIZES + [(333, 517)])
+def test_resize_down_and_up(gpu, orc, h, w):
+    rng = np.random.default_rng(h * 1000 + w)
+    src = (rng.random((h, w)) * 255).astype(np.float32)
+    want = orc.resize_scale(src, 0.8)
+    got = gpu.k_resize(src, inv_scale=0.8)
+    assert got.shape == want.shape
+    assert np.array_equal(got, want)
+    # flow upsample: explicit size, times 1/scaleStep
+    want_up = orc.resize_to(want, w, h) * np.float32(1 / 0.8)
+    got_up = gpu.k_resize(want, dw=w, dh=h, mul=float(np.float32(1 / 0.8)))
+    assert np.array_equal(got_up, want_up)
+
+
+@pytest.mark.parametrize("h,w", SIZES)
+def test_centered_gradient(gpu, orc, h, w):
+    rng = np.random.default_rng(1)
+    src = (rng.random((h, w)) * 255).astype(np.float32)
+    wx, wy = orc.centered_gradient(src)
+    gx, gy = gpu.k_centered_gradient(src)
+    assert np.array_equal(gx, wx) and np.array_equal(gy, wy)
+
+
+@pytest.mark.parametrize("h,w", SIZES)
+@pytest.mark.parametrize("amp", [0.7, 4.0, 60.0])
+def test_warp(gpu, orc, h, w, amp):
+    rng = np.random.default_rng(2)
+    I0 = (rng.random((h, w)) * 255).astype(np.float32)
+    I1 = (rng.random((h, w)) * 255).astype(np.float32)
+    I1x, I1y = orc.centered_gradient(I1)
+    u1, u2 = rnd(rng, h, w, amp), rnd(rng, h, w, amp)
+    _, wx, wy, g, r = orc.warp(I0, I1, I1x, I1y, u1, u2)
+    gx, gy, gg, gr = gpu.k_warp(I0, I1, I1x, I1y, u1, u2)
+    assert np.array_equal(gx, wx)
+    assert np.array_equal(gy, wy)
+    assert np.array_equal(gg, g)
+    assert np.array_equal(gr, r)
+
+
+@pytest.mark.parametrize("h,w", SIZES)
+def test_median5(gpu, orc, h, w):
+    rng = np.random.default_rng(3)
+    src = rnd(rng, h, w, 3.0)
+    assert np.array_equal(gpu.k_median5(src), orc.median5(src))
+
+
+def make_iter_inputs(rng, h, w):
+    I1wx, I1wy = rnd(rng, h, w, 8.0), rnd(rng, h, w, 8.0)
+    # some exactly-zero gradients to reach the `grad > FLT_EPSILON` branch
+    z = rng.random((h, w)) < 0.05
+    I1wx[z] = 0
+    I1wy[z] = 0
+    grad = I1wx * I1wx + I1wy * I1wy
+    rho_c = rnd(rng, h, w, 20.0)
+    state = [rnd(rng, h, w, 0.8) for _ in range(2)] + [rnd(rng, h, w, 0.4) for _ in range(4)]
+    return (I1wx, I1wy, grad, rho_c), state
+
+
+@pytest.mark.parametrize("h,w", SIZES)
+@pytest.mark.parametrize("n", [1, 2, 7])
+def test_iterate(gpu, orc, h, w, n):
+    rng = np.random.default_rng(4)
+    consts, state = make_iter_inputs(rng, h, w)
+    l_t, theta, taut = np.float32(0.15 * 0.3), np.float32(0.3), np.float32(0.25 / 0.3)
+    want = [s.copy() for s in state]
+    werr = [orc.iterate(*consts, *want, l_t, theta, taut) for _ in range(n)]
+    got = gpu.k_iterate(*consts, *state, l_t, theta, taut, n=n)
+    names = ["u1", "u2", "p11", "p12", "p21", "p22"]
+    for k in range(6):
+        assert np.array_equal(got[k], want[k]), names[k]
+    np.testing.assert_allclose(got[6], werr, rtol=1e-12)

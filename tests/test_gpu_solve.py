@@ -1,0 +1,76 @@
+"""Whole-pair parity through the C ABI (tvl1_calc_u8_host) against the C oracle.
+Tolerance from BASELINE.json north_star: mean EPE <= 0.01 px, max <= 0.1 px; in practice the
+two are bit-identical because every stage is."""
+import numpy as np
+import pytest
+
+from fibsem_optflow_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+MEAN_EPE_TOL = 0.01
+MAX_EPE_TOL = 0.1
+
+
+def run_pair(gpu, orc, I0, I1, **kw):
+    s = gpu.Solver(gpu.default_params(**kw))
+    u, v = s.calc(I0, I1)
+    okw = {("lambda" if k == "lambda_" else k): val for k, val in kw.items() if k != "iterations"}
+    okw.setdefault("inner_iterations", s.params.inner_iterations or 30)
+    ou, ov, oit, olev = orc.tvl1_calc(I0, I1, **okw)
+    return s, (u, v), (ou, ov, oit, olev)
+
+
+@pytest.mark.parametrize("h,w,seed", [(256, 320, 7), (300, 200, 3), (64, 48, 5)])
+def test_pair_defaults(gpu, orc, h, w, seed):
+    I0, I1 = synth.make_pair(h, w, seed=seed)
+    s, (u, v), (ou, ov, oit, olev) = run_pair(gpu, orc, I0, I1, lambda_=0.15, nscales=5,
+                                             inner_iterations=30, outer_iterations=10)
+    assert s.stats.levels == olev
+    assert np.array_equal(s.stats.iters_array(), oit[:olev])
+    epe = np.hypot(u - ou, v - ov)
+    assert epe.mean() <= MEAN_EPE_TOL and epe.max() <= MAX_EPE_TOL
+    assert np.array_equal(u, ou) and np.array_equal(v, ov)
+
+
+def test_pair_reference_wrapper_defaults(gpu, orc):
+    # generate_TV_args defaults: lambda .05, nscales 10, iterations 300 (src/optflow.cpp:503-511)
+    I0, I1 = synth.make_pair(200, 260, seed=9)
+    s = gpu.Solver(gpu.default_params())
+    u, v = s.calc(I0, I1)
+    ou, ov, oit, olev = orc.tvl1_calc(I0, I1, **{"lambda": 0.05, "nscales": 10})
+    assert s.stats.levels == olev
+    assert np.array_equal(s.stats.iters_array(), oit[:olev])
+    epe = np.hypot(u - ou, v - ov)
+    assert epe.mean() <= MEAN_EPE_TOL and epe.max() <= MAX_EPE_TOL
+
+
+def test_pair_no_median_flat(gpu, orc):
+    I0, I1 = synth.make_pair(128, 160, seed=2)
+    s, (u, v), (ou, ov, oit, olev) = run_pair(gpu, orc, I0, I1, lambda_=0.15, nscales=4, warps=3,
+                                             median_filtering=1, inner_iterations=40,
+                                             outer_iterations=2)
+    assert np.array_equal(s.stats.iters_array(), oit[:olev])
+    assert np.array_equal(u, ou) and np.array_equal(v, ov)
+
+
+def test_handle_reuse_and_resize(gpu, orc):
+    s = gpu.Solver(gpu.default_params(lambda_=0.15, nscales=3))
+    for (h, w, seed) in [(96, 128, 1), (96, 128, 2), (70, 90, 3)]:
+        I0, I1 = synth.make_pair(h, w, seed=seed)
+        u, v = s.calc(I0, I1)
+        ou, ov, _, _ = orc.tvl1_calc(I0, I1, **{"lambda": 0.15, "nscales": 3})
+        assert np.array_equal(u, ou) and np.array_equal(v, ov)
+
+
+def test_errors(gpu):
+    import ctypes as C
+    p = gpu.default_params()
+    p.nscales = 0
+    h = C.c_void_p()
+    assert gpu.lib().tvl1_create(C.byref(p), 0, C.byref(h)) == -1
+    p = gpu.default_params(gamma=0.5)
+    assert gpu.lib().tvl1_create(C.byref(p), 0, C.byref(h)) == -3
+    s = gpu.Solver(gpu.default_params())
+    with pytest.raises(gpu.Tvl1Error):
+        s.calc(np.zeros((8, 8), np.uint8), np.zeros((8, 9), np.uint8))
