@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""bench.py -- TV-L1 flow throughput on synthetic FIB-SEM-like slice pairs.
+
+    python bench.py --gpus N --steps K --warmup W            (N > 1: launched under torchrun)
+    python bench.py --impl reference --steps K --warmup W    (CPU restatement, host cores)
+
+A "step" is one pass of the hot path (pyramid -> per-level warp / median / primal-dual
+iterations -> flow) over one slice pair per GPU.  Workload = BASELINE.json configs[1]: one
+8192x8192 8-bit pair, 6 scales, 5 warps, DualTVL1 CPU-class defaults otherwise.  Slice pairs
+are independent, so N GPUs run N different pairs with no collective ("scaling": "weak").
+
+One JSON line on stdout (rank 0):
+  value     Mpx/s with the frames already resident in HBM (tvl1_calc_u8, CUDA events)
+  e2e       Mpx/s through the host-buffer C-ABI call (tvl1_calc_u8_host): H2D of both frames
+            from pinned memory and D2H of both flow planes inside the timed region
+  roofline  the primal-dual iteration kernel (k_iterate): 64 B/px/iteration
+            x the px-iterations it executed / its CUDA-event time inside the timed region
+  cpu_baseline  the C oracle (oracle/, OpenMP) on a bounded crop of the same pair
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from fibsem_optflow_b200 import synth  # noqa: E402
+
+METRIC = "tvl1_flow_mpx_per_s"
+UNIT = "Mpx/s"
+CPU_CROP = 2048          # the CPU legs run a CPU_CROP^2 crop of the pair (bounded sample)
+
+
+def workload(args):
+    return {"workload": "configs[1]: single %dx%d 8-bit slice pair, %d scales, %d warps" % (
+                args.size, args.size, args.scales, args.warps),
+            "width": args.size, "height": args.size, "nscales": args.scales, "warps": args.warps,
+            "tau": 0.25, "lambda": 0.15, "theta": 0.3, "epsilon": 0.01, "scaleStep": 0.8,
+            "innerIterations": 30, "outerIterations": 10, "medianFiltering": 5,
+            "pairs_per_gpu_per_step": 1, "sharding": "by pair, no collective",
+            "l2": "inputs larger than L2 (%.1f GB of planes per pair)" % (
+                args.size * args.size * 4 * 24 / 1e9)}
+
+
+def make_pair(args, rank):
+    return synth.make_pair(args.size, args.size, seed=7 + rank, dx=1.3, dy=-0.7,
+                           shear=4.0 / args.size)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        self.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def cpu_leg(args, steps, warmup, crop=CPU_CROP):
+    """The C oracle on the box's host cores, on a crop of the workload's pair."""
+    from oracle import oracle as O
+    I0, I1 = make_pair(args, 0)
+    n = min(crop, args.size)
+    o = (args.size - n) // 2
+    c0 = np.ascontiguousarray(I0[o:o + n, o:o + n])
+    c1 = np.ascontiguousarray(I1[o:o + n, o:o + n])
+    cores = os.cpu_count() or 1
+    p = O.default_params(nscales=args.scales, warps=args.warps, nthreads=cores)
+    times = []
+    iters = None
+    for i in range(warmup + steps):
+        t = time.perf_counter()
+        _, _, iters, _ = O.tvl1_calc(c0, c1, params=p)
+        dt = time.perf_counter() - t
+        if i >= warmup:
+            times.append(dt)
+    total = sum(times)
+    return {"value": n * n * len(times) / total / 1e6, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "center %dx%d crop of the %dx%d pair, same parameters, %d step(s), "
+                      "%d total iterations" % (n, n, args.size, args.size, len(times),
+                                               int(iters[iters >= 0].sum())),
+            "ms_per_step": total / len(times) * 1e3}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    cb = cpu_leg(args, steps, min(warmup, 1))
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT,
+            "n_gpus": args.gpus, "steps": steps, "warmup": min(warmup, 1),
+            "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload(args), "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+            "note": "CPU restatement of OpenCV DualTVL1 (oracle/tvl1_oracle.c, OpenMP); OpenCV's own "
+                    "class is not installable here (BASELINE.md section 2)"}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def run_ours(args):
+    import torch
+    from fibsem_optflow_b200 import _native as N
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU path "
+                         "(use --impl reference for the CPU restatement)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def allmax(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allsum(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    K, W = max(1, args.steps), max(3, args.warmup)
+    S = args.size
+    I0, I1 = make_pair(args, rank)
+    solver = N.Solver(N.default_params(lambda_=0.15, nscales=args.scales, warps=args.warps,
+                                       inner_iterations=30, outer_iterations=10), device=local)
+    # device-resident inputs / outputs (torch only allocates and hands out pointers)
+    d0 = torch.from_numpy(I0).cuda()
+    d1 = torch.from_numpy(I1).cuda()
+    du = torch.empty((S, S), dtype=torch.float32, device="cuda")
+    dv = torch.empty((S, S), dtype=torch.float32, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step_dev():
+        solver.calc_device(d0.data_ptr(), S, d1.data_ptr(), S, S, S, du.data_ptr(), dv.data_ptr(),
+                           S * 4, stream)
+
+    for _ in range(W):
+        step_dev()
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    it_ms, it_px, launches, tot_iters = 0.0, 0, 0, 0
+    lvl_ms = np.zeros(N.MAX_LEVELS)
+    lvl_pxit = np.zeros(N.MAX_LEVELS)
+    for _ in range(K):
+        step_dev()
+        st = solver.stats
+        it_ms += st.ms_iterate
+        it_px += st.px_iterations
+        launches += st.launches
+        tot_iters += st.total_iterations
+        its = st.iters_array()
+        for l in range(st.levels):
+            lvl_ms[l] += st.ms_iterate_level[l]
+            lvl_pxit[l] += float(st.width[l]) * st.height[l] * int(its[l].sum())
+    e1.record()
+    barrier()
+    ms_dev = allmax(e0.elapsed_time(e1))
+    clocks = sampler.stop()
+    stats = solver.stats
+    levels = stats.level_sizes()
+    iters_last = stats.iters_array().tolist()
+    alg_bytes = stats.algorithmic_bytes
+
+    # end to end: pinned host buffers -> tvl1_calc_u8_host (H2D + solve + D2H)
+    h0 = torch.from_numpy(I0).pin_memory()
+    h1 = torch.from_numpy(I1).pin_memory()
+    hu = torch.empty((S, S), dtype=torch.float32).pin_memory()
+    hv = torch.empty((S, S), dtype=torch.float32).pin_memory()
+
+    def step_host():
+        N.check(N.lib().tvl1_calc_u8_host(solver.handle, h0.data_ptr(), S, h1.data_ptr(), S, S, S,
+                                          hu.data_ptr(), hv.data_ptr(), S * 4, C.byref(solver.stats)))
+
+    step_host()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        step_host()
+    barrier()
+    ms_e2e = allmax((time.perf_counter() - t0) * 1e3)
+    checksum = float(hu[::257, ::263].double().sum() + hv[::257, ::263].double().sum())
+
+    px_all = allsum(float(S) * S * K)
+    total_launches = int(allsum(float(launches)))
+    if rank == 0:
+        peak, peak_src = peaks()
+        ach = 64.0 * it_px / (it_ms * 1e-3) / 1e9 if it_ms > 0 else 0.0
+        per_level = []
+        for l, (w, h) in enumerate(levels):
+            if lvl_ms[l] > 0:
+                per_level.append({"level": l, "size": [w, h],
+                                  "gbs": round(64.0 * lvl_pxit[l] / (lvl_ms[l] * 1e-3) / 1e9, 1),
+                                  "ms": round(lvl_ms[l] / K, 3)})
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "k_iterate_traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        line = {
+            "metric": METRIC, "value": px_all / (ms_dev * 1e-3) / 1e6, "unit": UNIT,
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_dev / K,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload(args),
+            "e2e": {"value": px_all / (ms_e2e * 1e-3) / 1e6, "unit": UNIT,
+                    "h2d_bytes_per_step": 2 * S * S, "d2h_bytes_per_step": 8 * S * S,
+                    "ms_per_step": ms_e2e / K, "api": "tvl1_calc_u8_host (pinned host buffers)",
+                    "checksum": checksum},
+            "gpu_launches": total_launches,
+            "roofline": {"bound": "hbm", "kernel": "k_iterate (all levels, inside the timed region)",
+                         "achieved": ach, "peak": peak, "unit": "GB/s",
+                         "frac": ach / peak if peak else None, "traffic": traffic,
+                         "peak_source": peak_src, "bytes_per_px_iteration": 64,
+                         "px_iterations_per_step": it_px / K, "kernel_ms_per_step": it_ms / K,
+                         "launch_bytes_level0": 64.0 * levels[0][0] * levels[0][1],
+                         "per_level": per_level,
+                         "pair_algorithmic_gbs": alg_bytes / (ms_dev / K * 1e-3) / 1e9},
+            "clocks": clocks,
+            "iterations_per_pair": int(tot_iters / K), "iters_last_pair": iters_last,
+            "stage_ms_last_pair": {"total": stats.ms_total, "pyramid": stats.ms_pyramid,
+                                   "warp": stats.ms_warp, "iterate": stats.ms_iterate,
+                                   "median": stats.ms_median, "other": stats.ms_other},
+        }
+        if world == 1 and not args.no_cpu:
+            cb = cpu_leg(args, 1, 0)
+            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line), flush=True)
+    solver.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--size", type=int, default=8192)
+    ap.add_argument("--scales", type=int, default=6)
+    ap.add_argument("--warps", type=int, default=5)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -5,7 +5,7 @@ import numpy as np
 from fibsem_optflow_b200 import _native as N, synth
 
 def run(h, w, nscales, reps=2):
-    t = time.time(); I0, I1 = synth.make_pair(h, w, seed=7); tg = time.time() - t
+    t = time.time(); I0, I1 = synth.make_pair(h, w, seed=7, shear=4.0/h); tg = time.time() - t
     s = N.Solver(N.default_params(lambda_=0.15, nscales=nscales, inner_iterations=30, outer_iterations=10))
     for r in range(reps):
         t = time.time(); u, v = s.calc(I0, I1); dt = time.time() - t
@@ -19,7 +19,7 @@ def run(h, w, nscales, reps=2):
             ms = st.ms_iterate_level[l]
             if ms > 0:
                 print(f"   L{l} {st.width[l]}x{st.height[l]} iters {its[l].tolist()} iter-ms {ms:.2f}  {64.0*px*n/ms/1e6:.0f} GB/s  ({ms/n*1e3:.1f} us/iter)")
-    ut, vt = synth.true_flow(h, w)
+    ut, vt = synth.true_flow(h, w, shear=4.0/h)
     epe = np.hypot(u-ut, v-vt)
     print(f"   EPE vs truth mean {epe.mean():.4f} interior max {epe[16:-16,16:-16].max():.4f}")
     s.close()

@@ -1,0 +1,187 @@
+"""Pins the C oracle (oracle/tvl1_oracle.c): against the committed golden vectors made from
+cv2 / glibc (tests/golden/make_golden.py) and against the live cv2 when it is importable."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def prim():
+    return np.load(os.path.join(GOLD, "primitives.npz"))
+
+
+@pytest.fixture(scope="module")
+def known():
+    with open(os.path.join(GOLD, "known_answers.json")) as f:
+        return json.load(f)
+
+
+def test_median_network_exhaustive(orc):
+    # 0/1 principle over all 2^25 inputs
+    assert orc.lib().orc_median25_selftest() == 0
+
+
+def test_remap_golden(orc, prim):
+    assert np.array_equal(orc.remap_cubic(prim["src"], prim["mx"], prim["my"]), prim["remap"])
+
+
+def test_resize_golden(orc, prim):
+    down = orc.resize_scale(prim["src"], 0.8)
+    assert np.array_equal(down, prim["down"])
+    h, w = prim["src"].shape
+    assert np.array_equal(orc.resize_to(prim["down"], w, h), prim["up"])
+
+
+def test_median_golden(orc, prim):
+    assert np.array_equal(orc.median5(prim["med_in"]), prim["med"])
+
+
+def test_resize_sizes(orc, known):
+    for n, want in known["resize_sizes_0.8"].items():
+        assert orc.scaled_size(int(n), 0.8) == want
+    # half-to-even
+    assert [orc.scaled_size(n, 0.5) for n in (5, 7, 9, 11)] == [2, 4, 4, 6]
+
+
+def test_pyramid_stop_rule(orc):
+    assert [s[0] for s in orc.pyramid_sizes(2048, 2048, 5, 0.8)] == [2048, 1638, 1310, 1048, 838]
+    # 20 -> 16 is kept, 19 -> 15 is built then dropped
+    assert len(orc.pyramid_sizes(20, 20, 5, 0.8)) == 2
+    assert len(orc.pyramid_sizes(19, 19, 5, 0.8)) == 1
+    # reference wrapper default nscales = 10 on a small tile
+    assert len(orc.pyramid_sizes(96, 128, 10, 0.8)) == 9
+
+
+def test_centered_gradient_edges(orc):
+    a = np.arange(20, dtype=np.float32).reshape(4, 5) ** 2
+    dx, dy = orc.centered_gradient(a)
+    assert dx[1, 0] == np.float32(0.5) * (a[1, 1] - a[1, 0])
+    assert dx[1, 4] == np.float32(0.5) * (a[1, 4] - a[1, 3])
+    assert dy[0, 2] == np.float32(0.5) * (a[1, 2] - a[0, 2])
+    assert dy[3, 2] == np.float32(0.5) * (a[3, 2] - a[2, 2])
+    assert dx[2, 2] == np.float32(0.5) * (a[2, 3] - a[2, 1])
+
+
+def test_random_shuffle_known_answer(orc, known):
+    # one set pixel per element so that loc[] == 0..11; unseeded rand() (reference debug mode)
+    import subprocess, sys
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "import numpy as np\n"
+        "from oracle import oracle as O\n"
+        "f = np.full((1, 12), 255, np.uint8); z = np.zeros((1, 12), np.float32)\n"
+        "r = O.random_points(f, f, z, z, scale=1.0, npoints=12, seed=-1)\n"
+        "print(r[5][:, 0].tolist())\n" % os.path.dirname(os.path.dirname(GOLD)))
+    out = subprocess.check_output([sys.executable, "-c", code]).decode()
+    assert json.loads(out) == known["glibc_rand"]["shuffle12_unseeded"]
+
+
+def test_match_arithmetic(orc, known):
+    m = known["match_arith"]
+    u = np.full((1, 101), m["flow"], np.float32)
+    px, py, qx, qy = orc.points_at(u, u, [[100, 0]], roi0=(7, 0), roi1=(7, 0),
+                                   scale=1.0 / m["inv_scale"])
+    assert qx[0] == m["q"]
+    assert px[0] == (100 + 7) * m["inv_scale"]
+
+
+def test_random_points_empty_mask(orc):
+    f = np.ones((4, 5), np.uint8)   # <= 1 everywhere -> empty mask
+    z = np.zeros((4, 5), np.float32)
+    px, py, qx, qy, w, pos = orc.random_points(f, f, z, z, npoints=25, seed=1)
+    assert px.tolist() == [-1.0] and qy.tolist() == [-1.0] and w.tolist() == [0.0]
+
+
+def test_mask_flow(orc):
+    f1 = np.array([[0, 1, 2, 255]], np.uint8)
+    u = np.ones((1, 4), np.float32)
+    v = np.ones((1, 4), np.float32)
+    orc.mask_flow(f1, u, v)
+    assert u.tolist() == [[0, 0, 1, 1]] and v.tolist() == [[0, 0, 1, 1]]
+
+
+def test_error_sum_modes_agree_on_small(orc):
+    from fibsem_optflow_b200 import synth
+    I0, I1 = synth.make_pair(64, 80, seed=4)
+    a = orc.tvl1_calc(I0, I1, nscales=3)
+    b = orc.tvl1_calc(I0, I1, nscales=3, error_sum_mode=1)
+    # the serial-fp32 sum (OpenCV literal) and the fp64 sum stop at the same iterations here
+    assert np.array_equal(a[2], b[2])
+    assert np.array_equal(a[0], b[0])
+
+
+def test_thread_count_invariance(orc):
+    from fibsem_optflow_b200 import synth
+    I0, I1 = synth.make_pair(72, 100, seed=5)
+    a = orc.tvl1_calc(I0, I1, nscales=3, nthreads=1)
+    b = orc.tvl1_calc(I0, I1, nscales=3, nthreads=4)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+
+
+def test_pair_golden(orc):
+    g = np.load(os.path.join(GOLD, "pair_96x128.npz"))
+    u, v, it, lev = orc.tvl1_calc(g["I0"], g["I1"])
+    assert np.array_equal(it[:lev], g["iters"])
+    assert np.array_equal(u, g["u"]) and np.array_equal(v, g["v"])
+    u, v, it, lev = orc.tvl1_calc(g["I0"], g["I1"], **{"lambda": 0.05, "nscales": 10})
+    assert np.array_equal(it[:lev], g["iters_ref"])
+    assert np.array_equal(u, g["u_ref"]) and np.array_equal(v, g["v_ref"])
+
+
+# ---- live cv2 (present in this image; skipped elsewhere)
+
+cv2 = pytest.importorskip("cv2")
+
+
+@pytest.fixture()
+def cv2_plain():
+    cv2.setUseOptimized(False)
+    yield cv2
+    cv2.setUseOptimized(True)
+
+
+@pytest.mark.parametrize("h,w", [(33, 47), (100, 131), (256, 256)])
+def test_primitives_vs_live_cv2(orc, cv2_plain, h, w):
+    rng = np.random.default_rng(h + w)
+    src = (rng.random((h, w)) * 255).astype(np.float32)
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+    for amp in (0.8, 5.0, 90.0):
+        mx = (xx + rng.standard_normal((h, w)) * amp).astype(np.float32)
+        my = (yy + rng.standard_normal((h, w)) * amp).astype(np.float32)
+        assert np.array_equal(orc.remap_cubic(src, mx, my), cv2.remap(src, mx, my, cv2.INTER_CUBIC))
+    down = cv2.resize(src, None, fx=0.8, fy=0.8, interpolation=cv2.INTER_LINEAR)
+    assert np.array_equal(orc.resize_scale(src, 0.8), down)
+    assert np.array_equal(orc.resize_to(down, w, h), cv2.resize(down, (w, h), interpolation=cv2.INTER_LINEAR))
+    m = (rng.standard_normal((h, w)) * 3).astype(np.float32)
+    assert np.array_equal(orc.median5(m), cv2.medianBlur(m, 5))
+
+
+def test_whole_pair_vs_cv2_composition(orc, cv2_plain):
+    from fibsem_optflow_b200 import synth
+    from oracle import tvl1_ref
+    I0, I1 = synth.make_pair(120, 150, seed=11)
+    u, v, it, lev = orc.tvl1_calc(I0, I1)
+    ru, rv, rit = tvl1_ref.tvl1_calc(I0, I1)
+    assert np.array_equal(it[:lev], rit)
+    assert np.array_equal(u, ru) and np.array_equal(v, rv)
+
+
+def test_iterate_vs_numpy(orc):
+    from oracle import tvl1_ref
+    rng = np.random.default_rng(8)
+    h, w = 41, 67
+    f = lambda s: (rng.standard_normal((h, w)) * s).astype(np.float32)
+    I1wx, I1wy, rho_c = f(8), f(8), f(20)
+    grad = I1wx * I1wx + I1wy * I1wy
+    st = [f(0.8), f(0.8), f(0.4), f(0.4), f(0.4), f(0.4)]
+    l_t, theta, taut = np.float32(0.045), np.float32(0.3), np.float32(0.25 / 0.3)
+    want = tvl1_ref.iterate(I1wx, I1wy, grad, rho_c, *st, l_t, theta, taut)
+    got = [s.copy() for s in st]
+    err = orc.iterate(I1wx, I1wy, grad, rho_c, *got, l_t, theta, taut)
+    for k in range(6):
+        assert np.array_equal(got[k], want[k])
+    assert abs(err - want[6]) <= 1e-12 * abs(err)
