@@ -62,7 +62,7 @@ EXPORTS = [
     "tvl1_set_params", "tvl1_set_timing", "tvl1_calc_u8", "tvl1_calc_u8_host",
     "tvl1_mask_flow_u8", "tvl1_sample_matches", "tvl1_k_convert_u8", "tvl1_k_resize",
     "tvl1_k_centered_gradient", "tvl1_k_warp", "tvl1_k_iterate", "tvl1_k_median5",
-    "tvl1_pyramid_sizes", "tvl1_glibc_rand", "tvl1_dev_count", "tvl1_dev_alloc", "tvl1_dev_free",
+    "tvl1_pyramid_sizes", "tvl1_glibc_rand", "tvl1_selftest_arith", "tvl1_dev_count", "tvl1_dev_alloc", "tvl1_dev_free",
     "tvl1_dev_memset", "tvl1_dev_h2d", "tvl1_dev_d2h", "tvl1_dev_sync",
     "tvl1_host_alloc_pinned", "tvl1_host_free_pinned",
 ]
@@ -110,6 +110,7 @@ def lib():
     L.tvl1_k_median5.argtypes = [_vp, C.c_int, C.c_int, C.c_int, _vp, _vp]
     L.tvl1_pyramid_sizes.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, _vp, _vp]
     L.tvl1_glibc_rand.argtypes = [C.c_longlong, C.c_longlong, C.c_int, _vp]
+    L.tvl1_selftest_arith.argtypes = [C.c_longlong, C.c_uint, C.c_int, C.c_int, C.POINTER(C.c_longlong)]
     L.tvl1_dev_alloc.argtypes = [C.c_int, _sz, C.POINTER(_vp)]
     L.tvl1_dev_free.argtypes = [C.c_int, _vp]
     L.tvl1_dev_memset.argtypes = [_vp, C.c_int, _sz]
@@ -157,6 +158,12 @@ def pyramid_sizes(w, h, nscales, scale_step):
     hs = (C.c_int * (MAX_LEVELS + 1))()
     n = check(lib().tvl1_pyramid_sizes(w, h, nscales, scale_step, ws, hs))
     return [(ws[i], hs[i]) for i in range(n)]
+
+
+def selftest_arith(n, seed=1, elo=-30, ehi=30):
+    bad = C.c_longlong(-1)
+    check(lib().tvl1_selftest_arith(n, seed, elo, ehi, C.byref(bad)))
+    return bad.value
 
 
 def glibc_rand(seed, skip, n):

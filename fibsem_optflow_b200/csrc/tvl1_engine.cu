@@ -125,32 +125,48 @@ int launch_warp(const WarpArgs& a, cudaStream_t st)
 
 static const int ITER_NW = 4;
 
-// rows per strip: tall strips amortise the bottom-halo row, short ones keep small levels
-// spread over all 148 SMs
-static int iterate_rows(int w, int h)
+// resident blocks of k_iterate on this device (SMs x occupancy), queried once
+static int iterate_resident_blocks()
 {
+    static int cached = 0;
+    if (cached) return cached;
+    int dev = 0, sms = 148, occ = 4;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_iterate<ITER_NW>, 32 * ITER_NW, 0) != cudaSuccess || occ < 1)
+        occ = 4;
+    cached = sms * occ;
+    return cached;
+}
+
+size_t iterate_max_blocks(int, int) { return 148 * 32 * 2; }
+
+// rows per tile: tall tiles amortise the bottom-halo row (R/(R+1)), but the tile count has to
+// divide evenly over the resident blocks (grid-stride loop, no partial last round)
+static int iterate_rows(int w, int h, int resident, int* grid)
+{
+    static const int cand[] = {4, 5, 6, 7, 8, 10, 12, 14, 16, 20, 24, 28, 32};
     const int gx = cdiv(cdiv(w, TVL1_STRIP), ITER_NW);
-    const int target = 148 * 4;
-    if (gx * cdiv(h, 16) >= target) return 16;
-    if (gx * cdiv(h, 8) >= target) return 8;
-    return 4;
-}
-
-size_t iterate_max_blocks(int w, int h)
-{
-    return (size_t)cdiv(cdiv(w, TVL1_STRIP), ITER_NW) * cdiv(h, 4);
-}
-
-int launch_iterate(const IterArgs& a, cudaStream_t st)
-{
-    const int R = iterate_rows(a.w, a.h);
-    dim3 b(32, ITER_NW);
-    dim3 g(cdiv(cdiv(a.w, TVL1_STRIP), ITER_NW), cdiv(a.h, R));
-    switch (R) {
-        case 16: k_iterate<16, ITER_NW><<<g, b, 0, st>>>(a); break;
-        case 8: k_iterate<8, ITER_NW><<<g, b, 0, st>>>(a); break;
-        default: k_iterate<4, ITER_NW><<<g, b, 0, st>>>(a); break;
+    double best = -1.0;
+    int best_r = 4, best_g = 1;
+    for (int R : cand) {
+        const long long ntiles = (long long)gx * cdiv(h, R);
+        const long long G = ntiles < resident ? ntiles : resident;
+        const long long rounds = (ntiles + G - 1) / G;
+        double eff = (double)ntiles / (double)(rounds * G) * (double)R / (double)(R + 1);
+        if (G < resident) eff *= (double)G / resident;   // not even one block per slot
+        if (eff >= best) { best = eff; best_r = R; best_g = (int)G; }
     }
+    *grid = best_g;
+    return best_r;
+}
+
+int launch_iterate(IterArgs& a, cudaStream_t st)
+{
+    int grid = 1;
+    a.rows = iterate_rows(a.w, a.h, iterate_resident_blocks(), &grid);
+    dim3 b(32, ITER_NW);
+    k_iterate<ITER_NW><<<grid, b, 0, st>>>(a);
     CK(cudaGetLastError());
     return TVL1_OK;
 }
@@ -158,7 +174,7 @@ int launch_iterate(const IterArgs& a, cudaStream_t st)
 int launch_median(const MedianArgs& a, int planes, cudaStream_t st)
 {
     dim3 b(32, 8);
-    dim3 g(cdiv(a.w, 32), cdiv(a.h, 8), planes);
+    dim3 g(cdiv(a.w, TVL1_MED_TW), cdiv(a.h, TVL1_MED_TH), planes);
     k_median5<<<g, b, 0, st>>>(a);
     CK(cudaGetLastError());
     return TVL1_OK;
@@ -379,7 +395,7 @@ static int calc_device(tvl1_handle* H, const uint8_t* f0, size_t pitch0, const u
         span_end();
 
         IterArgs ia;
-        ia.I1wx = H->I1wx; ia.I1wy = H->I1wy; ia.grad = H->grad; ia.rho_c = H->rho;
+        ia.I1wx = H->I1wx; ia.I1wy = H->I1wy; ia.rho_c = H->rho;
         ia.u1[0] = lv.u1; ia.u1[1] = H->u1x; ia.u2[0] = lv.u2; ia.u2[1] = H->u2x;
         for (int k = 0; k < 2; k++) { ia.p11[k] = H->p[0][k]; ia.p12[k] = H->p[1][k]; ia.p21[k] = H->p[2][k]; ia.p22[k] = H->p[3][k]; }
         ia.w = lv.w; ia.h = lv.h; ia.pitch = lv.pitch;
@@ -391,7 +407,7 @@ static int calc_device(tvl1_handle* H, const uint8_t* f0, size_t pitch0, const u
         WarpArgs wa;
         wa.I0 = lv.I0; wa.I1 = lv.I1; wa.I1x = H->I1x; wa.I1y = H->I1y;
         wa.u1[0] = lv.u1; wa.u1[1] = H->u1x; wa.u2[0] = lv.u2; wa.u2[1] = H->u2x;
-        wa.I1wx = H->I1wx; wa.I1wy = H->I1wy; wa.grad = H->grad; wa.rho_c = H->rho;
+        wa.I1wx = H->I1wx; wa.I1wy = H->I1wy; wa.grad = nullptr; wa.rho_c = H->rho;
         wa.w = lv.w; wa.h = lv.h; wa.pitch = lv.pitch; wa.level = s; wa.ctrl = H->d_ctrl;
 
         for (int wi = 0; wi < W; ++wi) {
@@ -682,7 +698,7 @@ int tvl1_k_iterate(const float* d_I1wx, const float* d_I1wy, const float* d_grad
     float* tw[6];
     for (int k = 0; k < 6; k++) tw[k] = (float*)(tmp + k * pb);
     IterArgs a;
-    a.I1wx = d_I1wx; a.I1wy = d_I1wy; a.grad = d_grad; a.rho_c = d_rho_c;
+    a.I1wx = d_I1wx; a.I1wy = d_I1wy; a.rho_c = d_rho_c;   // grad is recomputed in the kernel
     a.u1[0] = d_u1; a.u1[1] = tw[0]; a.u2[0] = d_u2; a.u2[1] = tw[1];
     a.p11[0] = d_p11; a.p11[1] = tw[2]; a.p12[0] = d_p12; a.p12[1] = tw[3];
     a.p21[0] = d_p21; a.p21[1] = tw[4]; a.p22[0] = d_p22; a.p22[1] = tw[5];
@@ -716,6 +732,21 @@ int tvl1_k_median5(const float* d_src, int w, int h, int pitch, float* d_dst, vo
     a.u1[0] = const_cast<float*>(d_src); a.u1[1] = d_dst; a.u2[0] = a.u2[1] = nullptr;
     a.w = w; a.h = h; a.pitch = pitch; a.level = -1; a.slot = 0; a.ctrl = nullptr;
     return launch_median(a, 1, (cudaStream_t)stream);
+}
+
+int tvl1_selftest_arith(long long n, unsigned seed, int elo, int ehi, long long* mismatches)
+{
+    if (!mismatches || n <= 0 || elo > ehi || elo < -126 || ehi > 127) return fail(TVL1_ERR_INVALID, "bad argument");
+    unsigned long long* d = nullptr;
+    CK(cudaMalloc(&d, sizeof(*d)));
+    cudaMemset(d, 0, sizeof(*d));
+    k_selftest_arith<<<148 * 8, 256>>>(seed, n, elo, ehi, d);
+    unsigned long long hres = 0;
+    cudaError_t e = cudaMemcpy(&hres, d, sizeof(hres), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(TVL1_ERR_CUDA, "selftest: %s", cudaGetErrorString(e));
+    *mismatches = (long long)hres;
+    return TVL1_OK;
 }
 
 int tvl1_pyramid_sizes(int w, int h, int nscales, double scale_step, int* ws, int* hs)

@@ -149,6 +149,11 @@ int tvl1_k_iterate(const float* d_I1wx, const float* d_I1wy, const float* d_grad
                    float l_t, float theta, float taut, int n, double* errors, void* stream);
 int tvl1_k_median5(const float* d_src, int w, int h, int pitch, float* d_dst, void* stream);
 
+/* Self-test of the kernels' exact fast paths (reciprocal-sharing division, fused hypot) against
+ * the IEEE operators on n pseudo-random operand triples with binary exponents in [elo, ehi];
+ * *mismatches receives the number of differing results (must be 0). */
+int tvl1_selftest_arith(long long n, unsigned seed, int elo, int ehi, long long* mismatches);
+
 /* pyramid level sizes for (w, h): returns levels used (A.2 stop rule) */
 int tvl1_pyramid_sizes(int w, int h, int nscales, double scale_step, int* ws, int* hs);
 
