@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "csrc", "libtvl1_b200.so")
+SO_PATH = os.environ.get("TVL1_SO") or os.path.join(_HERE, "csrc", "libtvl1_b200.so")   # TVL1_SO: developer builds
 
 MAX_LEVELS = 32
 MAX_WARPS = 64
@@ -61,7 +61,7 @@ EXPORTS = [
     "tvl1_version", "tvl1_last_error", "tvl1_default_params", "tvl1_create", "tvl1_destroy",
     "tvl1_set_params", "tvl1_set_timing", "tvl1_calc_u8", "tvl1_calc_u8_host",
     "tvl1_mask_flow_u8", "tvl1_sample_matches", "tvl1_k_convert_u8", "tvl1_k_resize",
-    "tvl1_k_centered_gradient", "tvl1_k_warp", "tvl1_k_iterate", "tvl1_k_median5",
+    "tvl1_k_centered_gradient", "tvl1_k_warp", "tvl1_k_iterate", "tvl1_k_median5", "tvl1_k_last_ms",
     "tvl1_pyramid_sizes", "tvl1_glibc_rand", "tvl1_selftest_arith", "tvl1_dev_count", "tvl1_dev_alloc", "tvl1_dev_free",
     "tvl1_dev_memset", "tvl1_dev_h2d", "tvl1_dev_d2h", "tvl1_dev_sync",
     "tvl1_host_alloc_pinned", "tvl1_host_free_pinned",
@@ -104,10 +104,11 @@ def lib():
     L.tvl1_k_resize.argtypes = [_vp, C.c_int, C.c_int, C.c_int, _vp, C.c_int, C.c_int, C.c_int,
                                 C.c_double, C.c_float, _vp]
     L.tvl1_k_centered_gradient.argtypes = [_vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp]
-    L.tvl1_k_warp.argtypes = [_vp] * 6 + [C.c_int, C.c_int, C.c_int] + [_vp] * 5
+    L.tvl1_k_warp.argtypes = [_vp] * 4 + [C.c_int, C.c_int, C.c_int] + [_vp] * 6
     L.tvl1_k_iterate.argtypes = [_vp] * 10 + [C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
                                               C.c_float, C.c_int, _vp, _vp]
     L.tvl1_k_median5.argtypes = [_vp, C.c_int, C.c_int, C.c_int, _vp, _vp]
+    L.tvl1_k_last_ms.argtypes = [C.POINTER(C.c_float)]
     L.tvl1_pyramid_sizes.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, _vp, _vp]
     L.tvl1_glibc_rand.argtypes = [C.c_longlong, C.c_longlong, C.c_int, _vp]
     L.tvl1_selftest_arith.argtypes = [C.c_longlong, C.c_uint, C.c_int, C.c_int, C.POINTER(C.c_longlong)]
@@ -158,6 +159,12 @@ def pyramid_sizes(w, h, nscales, scale_step):
     hs = (C.c_int * (MAX_LEVELS + 1))()
     n = check(lib().tvl1_pyramid_sizes(w, h, nscales, scale_step, ws, hs))
     return [(ws[i], hs[i]) for i in range(n)]
+
+
+def k_last_ms():
+    ms = C.c_float(0)
+    check(lib().tvl1_k_last_ms(C.byref(ms)))
+    return ms.value
 
 
 def selftest_arith(n, seed=1, elo=-30, ehi=30):
@@ -352,13 +359,14 @@ def k_centered_gradient(src, device=0):
     return dx.get(), dy.get()
 
 
-def k_warp(I0, I1, I1x, I1y, u1, u2, device=0):
+def k_warp(I0, I1, u1, u2, device=0):
+    """Returns I1w, I1wx, I1wy, grad, rho_c (the centred gradients of I1 are formed in-kernel)."""
     h, w = np.asarray(I0).shape
-    ins = [Plane(h, w, device, np.asarray(a, np.float32)) for a in (I0, I1, I1x, I1y, u1, u2)]
-    outs = [Plane(h, w, device) for _ in range(4)]
+    ins = [Plane(h, w, device, np.asarray(a, np.float32)) for a in (I0, I1, u1, u2)]
+    outs = [Plane(h, w, device) for _ in range(5)]
     check(lib().tvl1_k_warp(*[p.ptr for p in ins], w, h, ins[0].pitch, *[p.ptr for p in outs], None))
     check(lib().tvl1_dev_sync(device))
-    return tuple(p.get() for p in outs)   # I1wx, I1wy, grad, rho_c
+    return tuple(p.get() for p in outs)
 
 
 def k_iterate(I1wx, I1wy, grad, rho_c, u1, u2, p11, p12, p21, p22, l_t, theta, taut, n=1, device=0):

@@ -118,12 +118,16 @@ int launch_gradient(const float* src, int w, int h, int pitch, float* dx, float*
 int launch_warp(const WarpArgs& a, cudaStream_t st)
 {
     dim3 b(32, 8);
-    k_warp<<<grid2d(a.w, a.h, b), b, 0, st>>>(a);
+    dim3 g(cdiv(a.w, TVL1_WP_TW), cdiv(a.h, TVL1_WP_TH));
+    k_warp<<<g, b, 0, st>>>(a);
     CK(cudaGetLastError());
     return TVL1_OK;
 }
 
-static const int ITER_NW = 4;
+#ifndef TVL1_ITER_NW
+#define TVL1_ITER_NW 4
+#endif
+static const int ITER_NW = TVL1_ITER_NW;
 
 // resident blocks of k_iterate on this device (SMs x occupancy), queried once
 static int iterate_resident_blocks()
@@ -389,8 +393,6 @@ static int calc_device(tvl1_handle* H, const uint8_t* f0, size_t pitch0, const u
         const size_t pb = (size_t)lv.pitch * lv.h * sizeof(float);
         const float scaled_eps = (float)(P.epsilon * P.epsilon * (double)(lv.w * lv.h));
         if ((rc = span_begin(3, s))) return rc;
-        if ((rc = launch_gradient(lv.I1, lv.w, lv.h, lv.pitch, H->I1x, H->I1y, st))) return rc;
-        launches++;
         for (int k = 0; k < 4; k++) CK(cudaMemsetAsync(H->p[k][0], 0, pb, st));
         span_end();
 
@@ -405,9 +407,9 @@ static int calc_device(tvl1_handle* H, const uint8_t* f0, size_t pitch0, const u
         ma.u1[0] = lv.u1; ma.u1[1] = H->u1x; ma.u2[0] = lv.u2; ma.u2[1] = H->u2x;
         ma.w = lv.w; ma.h = lv.h; ma.pitch = lv.pitch; ma.level = s; ma.ctrl = H->d_ctrl;
         WarpArgs wa;
-        wa.I0 = lv.I0; wa.I1 = lv.I1; wa.I1x = H->I1x; wa.I1y = H->I1y;
+        wa.I0 = lv.I0; wa.I1 = lv.I1;
         wa.u1[0] = lv.u1; wa.u1[1] = H->u1x; wa.u2[0] = lv.u2; wa.u2[1] = H->u2x;
-        wa.I1wx = H->I1wx; wa.I1wy = H->I1wy; wa.grad = nullptr; wa.rho_c = H->rho;
+        wa.I1w = nullptr; wa.I1wx = H->I1wx; wa.I1wy = H->I1wy; wa.grad = nullptr; wa.rho_c = H->rho;
         wa.w = lv.w; wa.h = lv.h; wa.pitch = lv.pitch; wa.level = s; wa.ctrl = H->d_ctrl;
 
         for (int wi = 0; wi < W; ++wi) {
@@ -639,6 +641,23 @@ int tvl1_mask_flow_u8(tvl1_handle* H, const uint8_t* d_frame1, size_t pitch1, in
 
 // ---- stage-level entry points
 
+// CUDA-event bracket around the launches of the most recent stage-level call (tvl1_k_last_ms)
+static thread_local cudaEvent_t t_ev0 = nullptr, t_ev1 = nullptr;
+static void stage_begin(cudaStream_t st)
+{
+    if (!t_ev0) { cudaEventCreate(&t_ev0); cudaEventCreate(&t_ev1); }
+    cudaEventRecord(t_ev0, st);
+}
+static void stage_end(cudaStream_t st) { cudaEventRecord(t_ev1, st); }
+
+int tvl1_k_last_ms(float* ms)
+{
+    if (!ms || !t_ev0) return fail(TVL1_ERR_INVALID, "no stage-level call has been timed on this thread");
+    CK(cudaEventSynchronize(t_ev1));
+    CK(cudaEventElapsedTime(ms, t_ev0, t_ev1));
+    return TVL1_OK;
+}
+
 int tvl1_k_convert_u8(const uint8_t* d_src, size_t pitch_bytes, int w, int h, float* d_dst, int pitch, void* stream)
 {
     if (!d_src || !d_dst || w <= 0 || h <= 0 || pitch % 4) return fail(TVL1_ERR_INVALID, "bad argument");
@@ -658,23 +677,24 @@ int tvl1_k_centered_gradient(const float* d_src, int w, int h, int pitch, float*
     return launch_gradient(d_src, w, h, pitch, d_dx, d_dy, (cudaStream_t)stream);
 }
 
-int tvl1_k_warp(const float* d_I0, const float* d_I1, const float* d_I1x, const float* d_I1y, const float* d_u1,
-                const float* d_u2, int w, int h, int pitch, float* d_I1wx, float* d_I1wy, float* d_grad,
-                float* d_rho_c, void* stream)
+int tvl1_k_warp(const float* d_I0, const float* d_I1, const float* d_u1, const float* d_u2, int w, int h,
+                int pitch, float* d_I1w, float* d_I1wx, float* d_I1wy, float* d_grad, float* d_rho_c, void* stream)
 {
-    if (!d_I0 || !d_I1 || !d_I1x || !d_I1y || !d_u1 || !d_u2 || !d_I1wx || !d_I1wy || !d_grad || !d_rho_c ||
-        w <= 0 || h <= 0)
+    if (!d_I0 || !d_I1 || !d_u1 || !d_u2 || !d_I1wx || !d_I1wy || !d_rho_c || w <= 0 || h <= 0 || pitch % 2)
         return fail(TVL1_ERR_INVALID, "bad argument");
     int dev = 0;
     CK(cudaGetDevice(&dev));
     int rc = upload_cubic_table(dev);
     if (rc) return rc;
     WarpArgs a;
-    a.I0 = d_I0; a.I1 = d_I1; a.I1x = d_I1x; a.I1y = d_I1y;
+    a.I0 = d_I0; a.I1 = d_I1;
     a.u1[0] = a.u1[1] = d_u1; a.u2[0] = a.u2[1] = d_u2;
-    a.I1wx = d_I1wx; a.I1wy = d_I1wy; a.grad = d_grad; a.rho_c = d_rho_c;
+    a.I1w = d_I1w; a.I1wx = d_I1wx; a.I1wy = d_I1wy; a.grad = d_grad; a.rho_c = d_rho_c;
     a.w = w; a.h = h; a.pitch = pitch; a.level = -1; a.ctrl = nullptr;
-    return launch_warp(a, (cudaStream_t)stream);
+    stage_begin((cudaStream_t)stream);
+    rc = launch_warp(a, (cudaStream_t)stream);
+    stage_end((cudaStream_t)stream);
+    return rc;
 }
 
 int tvl1_k_iterate(const float* d_I1wx, const float* d_I1wy, const float* d_grad, const float* d_rho_c,
@@ -709,7 +729,9 @@ int tvl1_k_iterate(const float* d_I1wx, const float* d_I1wy, const float* d_grad
     a.partials = (double*)(tmp + part_off);
     a.errlog = (double*)(tmp + log_off);
     int rc = TVL1_OK;
+    stage_begin(st);
     for (int i = 0; i < n && !rc; i++) rc = launch_iterate(a, st);
+    stage_end(st);
     if (!rc && (n & 1)) {
         float* dst[6] = {d_u1, d_u2, d_p11, d_p12, d_p21, d_p22};
         for (int k = 0; k < 6 && !rc; k++)
@@ -731,7 +753,10 @@ int tvl1_k_median5(const float* d_src, int w, int h, int pitch, float* d_dst, vo
     MedianArgs a;
     a.u1[0] = const_cast<float*>(d_src); a.u1[1] = d_dst; a.u2[0] = a.u2[1] = nullptr;
     a.w = w; a.h = h; a.pitch = pitch; a.level = -1; a.slot = 0; a.ctrl = nullptr;
-    return launch_median(a, 1, (cudaStream_t)stream);
+    stage_begin((cudaStream_t)stream);
+    const int rc = launch_median(a, 1, (cudaStream_t)stream);
+    stage_end((cudaStream_t)stream);
+    return rc;
 }
 
 int tvl1_selftest_arith(long long n, unsigned seed, int elo, int ehi, long long* mismatches)

@@ -137,9 +137,11 @@ int tvl1_k_resize(const float* d_src, int sw, int sh, int spitch, float* d_dst, 
                   int dpitch, double inv_scale /* <= 0: explicit size */, float mul, void* stream);
 int tvl1_k_centered_gradient(const float* d_src, int w, int h, int pitch, float* d_dx,
                              float* d_dy, void* stream);
-int tvl1_k_warp(const float* d_I0, const float* d_I1, const float* d_I1x, const float* d_I1y,
-                const float* d_u1, const float* d_u2, int w, int h, int pitch,
-                float* d_I1wx, float* d_I1wy, float* d_grad, float* d_rho_c, void* stream);
+/* warp step; I1's centred gradients are formed inside (A.3 fused into A.4).  d_I1w and d_grad
+ * may be NULL. */
+int tvl1_k_warp(const float* d_I0, const float* d_I1, const float* d_u1, const float* d_u2,
+                int w, int h, int pitch, float* d_I1w, float* d_I1wx, float* d_I1wy,
+                float* d_grad, float* d_rho_c, void* stream);
 /* n inner iterations with no stop test; state planes are updated in place (the result
  * is copied back if it ends in the internal twin buffers).  errors (host, may be NULL)
  * receives the n per-iteration error sums. */
@@ -148,6 +150,9 @@ int tvl1_k_iterate(const float* d_I1wx, const float* d_I1wy, const float* d_grad
                    float* d_p21, float* d_p22, int w, int h, int pitch,
                    float l_t, float theta, float taut, int n, double* errors, void* stream);
 int tvl1_k_median5(const float* d_src, int w, int h, int pitch, float* d_dst, void* stream);
+/* CUDA-event time of the kernel launches of the calling thread's most recent tvl1_k_warp /
+ * tvl1_k_iterate / tvl1_k_median5 call (waits for them). */
+int tvl1_k_last_ms(float* ms);
 
 /* Self-test of the kernels' exact fast paths (reciprocal-sharing division, fused hypot) against
  * the IEEE operators on n pseudo-random operand triples with binary exponents in [elo, ehi];

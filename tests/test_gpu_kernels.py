@@ -50,8 +50,9 @@ def test_warp(gpu, orc, h, w, amp):
     I1 = (rng.random((h, w)) * 255).astype(np.float32)
     I1x, I1y = orc.centered_gradient(I1)
     u1, u2 = rnd(rng, h, w, amp), rnd(rng, h, w, amp)
-    _, wx, wy, g, r = orc.warp(I0, I1, I1x, I1y, u1, u2)
-    gx, gy, gg, gr = gpu.k_warp(I0, I1, I1x, I1y, u1, u2)
+    ww, wx, wy, g, r = orc.warp(I0, I1, I1x, I1y, u1, u2)
+    gw, gx, gy, gg, gr = gpu.k_warp(I0, I1, u1, u2)
+    assert np.array_equal(gw, ww)
     assert np.array_equal(gx, wx)
     assert np.array_equal(gy, wy)
     assert np.array_equal(gg, g)
