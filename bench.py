@@ -64,8 +64,15 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index = index
-        self.rows = []
+        self.rows = []      # (wall time, fields)
         self.proc = None
+        self.t0 = self.t1 = None
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def run(self):
         try:
@@ -74,7 +81,7 @@ class ClockSampler(threading.Thread):
                  "--format=csv,noheader,nounits", "-lms", "200"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
-                self.rows.append([c.strip() for c in line.split(",")])
+                self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
         except Exception:
             pass
 
@@ -84,7 +91,9 @@ class ClockSampler(threading.Thread):
         self.join(timeout=2)
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        inwin = [r for (t, r) in self.rows
+                 if self.t0 is None or (self.t0 - 0.05 <= t <= (self.t1 or t) + 0.25)]
+        for r in (inwin or [r for (_, r) in self.rows[-3:]]):
             try:
                 sm.append(float(r[1]))
                 mx.append(float(r[2]))
@@ -166,8 +175,10 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dist = None
     if world > 1:
+        # slice pairs are independent: no collective touches the data path, so the only
+        # cross-rank traffic is this control-plane barrier / MAX / SUM of three scalars (gloo)
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.init_process_group("gloo")
 
     def barrier():
         if dist is not None:
@@ -177,14 +188,14 @@ def run_ours(args):
     def allmax(x):
         if dist is None:
             return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        t = torch.tensor([x], dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
     def allsum(x):
         if dist is None:
             return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        t = torch.tensor([x], dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
@@ -204,11 +215,15 @@ def run_ours(args):
         solver.calc_device(d0.data_ptr(), S, d1.data_ptr(), S, S, S, du.data_ptr(), dv.data_ptr(),
                            S * 4, stream)
 
+    # nvidia-smi wants the physical index: honour CUDA_VISIBLE_DEVICES if the launcher set it
+    vis = [v for v in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if v.strip() != ""]
+    phys = vis[local].strip() if local < len(vis) else str(local)
+    sampler = ClockSampler(phys)
+    sampler.start()
     for _ in range(W):
         step_dev()
-    sampler = ClockSampler(local)
-    sampler.start()
     barrier()
+    sampler.mark_begin()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     it_ms, it_px, launches, tot_iters = 0.0, 0, 0, 0
@@ -227,8 +242,8 @@ def run_ours(args):
             lvl_pxit[l] += float(st.width[l]) * st.height[l] * int(its[l].sum())
     e1.record()
     barrier()
+    sampler.mark_end()
     ms_dev = allmax(e0.elapsed_time(e1))
-    clocks = sampler.stop()
     stats = solver.stats
     levels = stats.level_sizes()
     iters_last = stats.iters_array().tolist()
@@ -251,6 +266,8 @@ def run_ours(args):
         step_host()
     barrier()
     ms_e2e = allmax((time.perf_counter() - t0) * 1e3)
+    sampler.t1 = time.time()      # the clock window covers both timed regions
+    clocks = sampler.stop()
     checksum = float(hu[::257, ::263].double().sum() + hv[::257, ::263].double().sum())
 
     px_all = allsum(float(S) * S * K)

@@ -660,7 +660,8 @@ int tvl1_k_last_ms(float* ms)
 
 int tvl1_k_convert_u8(const uint8_t* d_src, size_t pitch_bytes, int w, int h, float* d_dst, int pitch, void* stream)
 {
-    if (!d_src || !d_dst || w <= 0 || h <= 0 || pitch % 4) return fail(TVL1_ERR_INVALID, "bad argument");
+    if (!d_src || !d_dst || w <= 0 || h <= 0 || pitch % 4 || pitch < w || pitch_bytes < (size_t)w)
+        return fail(TVL1_ERR_INVALID, "bad argument");
     return launch_convert(d_src, pitch_bytes, w, h, d_dst, pitch, (cudaStream_t)stream);
 }
 
@@ -680,7 +681,7 @@ int tvl1_k_centered_gradient(const float* d_src, int w, int h, int pitch, float*
 int tvl1_k_warp(const float* d_I0, const float* d_I1, const float* d_u1, const float* d_u2, int w, int h,
                 int pitch, float* d_I1w, float* d_I1wx, float* d_I1wy, float* d_grad, float* d_rho_c, void* stream)
 {
-    if (!d_I0 || !d_I1 || !d_u1 || !d_u2 || !d_I1wx || !d_I1wy || !d_rho_c || w <= 0 || h <= 0 || pitch % 2)
+    if (!d_I0 || !d_I1 || !d_u1 || !d_u2 || !d_I1wx || !d_I1wy || !d_rho_c || w <= 0 || h <= 0 || pitch % 4 || pitch < w)
         return fail(TVL1_ERR_INVALID, "bad argument");
     int dev = 0;
     CK(cudaGetDevice(&dev));
@@ -749,7 +750,8 @@ int tvl1_k_iterate(const float* d_I1wx, const float* d_I1wy, const float* d_grad
 
 int tvl1_k_median5(const float* d_src, int w, int h, int pitch, float* d_dst, void* stream)
 {
-    if (!d_src || !d_dst || d_src == d_dst || w <= 0 || h <= 0) return fail(TVL1_ERR_INVALID, "bad argument");
+    if (!d_src || !d_dst || d_src == d_dst || w <= 0 || h <= 0 || pitch % 4 || pitch < w)
+        return fail(TVL1_ERR_INVALID, "bad argument");
     MedianArgs a;
     a.u1[0] = const_cast<float*>(d_src); a.u1[1] = d_dst; a.u2[0] = a.u2[1] = nullptr;
     a.w = w; a.h = h; a.pitch = pitch; a.level = -1; a.slot = 0; a.ctrl = nullptr;
