@@ -249,6 +249,25 @@ def run_ours(args):
     iters_last = stats.iters_array().tolist()
     alg_bytes = stats.algorithmic_bytes
 
+    # this box's own copy bandwidth, measured the way MEASURED_PEAKS.json was (context only:
+    # boxes of the pool differ by ~20 %; roofline.frac stays against the driver-written peak)
+    copy_gbs = None
+    try:
+        ca = torch.empty(1 << 29, dtype=torch.bfloat16, device="cuda")
+        cb = torch.empty_like(ca)
+        best = 1e9
+        for _ in range(6):
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record()
+            cb.copy_(ca)
+            c1.record()
+            torch.cuda.synchronize()
+            best = min(best, c0.elapsed_time(c1))
+        copy_gbs = 2.0 * ca.numel() * 2 / (best * 1e-3) / 1e9
+        del ca, cb
+    except Exception:
+        pass
+
     # end to end: pinned host buffers -> tvl1_calc_u8_host (H2D + solve + D2H)
     h0 = torch.from_numpy(I0).pin_memory()
     h1 = torch.from_numpy(I1).pin_memory()
@@ -301,7 +320,9 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "kernel": "k_iterate (all levels, inside the timed region)",
                          "achieved": ach, "peak": peak, "unit": "GB/s",
                          "frac": ach / peak if peak else None, "traffic": traffic,
-                         "peak_source": peak_src, "bytes_per_px_iteration": 64,
+                         "peak_source": peak_src, "copy_gbs_this_box": copy_gbs,
+                         "frac_of_this_box_copy": (ach / copy_gbs) if copy_gbs else None,
+                         "bytes_per_px_iteration": 64,
                          "px_iterations_per_step": it_px / K, "kernel_ms_per_step": it_ms / K,
                          "launch_bytes_level0": 64.0 * levels[0][0] * levels[0][1],
                          "per_level": per_level,
