@@ -56,11 +56,22 @@ class Stats(C.Structure):
         return [(self.width[i], self.height[i]) for i in range(self.levels)]
 
 
+class StackIO(C.Structure):
+    _fields_ = [
+        ("h_slices", C.POINTER(C.c_void_p)), ("pitch", C.c_size_t),
+        ("n_slices", C.c_int), ("width", C.c_int), ("height", C.c_int), ("apply_mask", C.c_int),
+        ("h_u", C.POINTER(C.c_void_p)), ("h_v", C.POINTER(C.c_void_p)), ("pitch_out", C.c_size_t),
+        ("npoints", C.c_int), ("scale", C.c_float), ("seed", C.c_longlong),
+        ("px", C.c_void_p), ("py", C.c_void_p), ("qx", C.c_void_p), ("qy", C.c_void_p), ("w", C.c_void_p),
+        ("n_out", C.c_void_p), ("stats", C.POINTER(Stats)),
+    ]
+
+
 # every symbol include/tvl1_b200.h declares (checked by tests/test_abi.py)
 EXPORTS = [
     "tvl1_version", "tvl1_last_error", "tvl1_default_params", "tvl1_create", "tvl1_destroy",
     "tvl1_set_params", "tvl1_set_timing", "tvl1_calc_u8", "tvl1_calc_u8_host",
-    "tvl1_mask_flow_u8", "tvl1_sample_matches", "tvl1_k_convert_u8", "tvl1_k_resize",
+    "tvl1_mask_flow_u8", "tvl1_sample_matches", "tvl1_sample_matches_skip", "tvl1_stack_run", "tvl1_k_convert_u8", "tvl1_k_resize",
     "tvl1_k_centered_gradient", "tvl1_k_warp", "tvl1_k_iterate", "tvl1_k_median5", "tvl1_k_last_ms",
     "tvl1_pyramid_sizes", "tvl1_glibc_rand", "tvl1_selftest_arith", "tvl1_dev_count", "tvl1_dev_alloc", "tvl1_dev_free",
     "tvl1_dev_memset", "tvl1_dev_h2d", "tvl1_dev_d2h", "tvl1_dev_sync",
@@ -100,6 +111,7 @@ def lib():
                                       C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int,
                                       C.c_longlong, _vp, _vp, _vp, _vp, _vp, _vp,
                                       C.POINTER(C.c_int), _vp]
+    L.tvl1_stack_run.argtypes = [_vp, C.POINTER(StackIO), C.POINTER(C.c_float)]
     L.tvl1_k_convert_u8.argtypes = [_vp, _sz, C.c_int, C.c_int, _vp, C.c_int, _vp]
     L.tvl1_k_resize.argtypes = [_vp, C.c_int, C.c_int, C.c_int, _vp, C.c_int, C.c_int, C.c_int,
                                 C.c_double, C.c_float, _vp]
@@ -306,6 +318,58 @@ class Solver:
                                         pos.ctypes.data, C.byref(k), stream))
         k = k.value
         return px[:k], py[:k], qx[:k], qy[:k], wg[:k], pos[:k]
+
+    def run_stack(self, slices, flows=True, apply_mask=False, npoints=-1, scale=0.5, seed=-1,
+                  out_u=None, out_v=None, slice_ptrs=None, pitch=None, shape=None):
+        """Pairs (k, k+1) of a stack of uint8 slices (tvl1_stack_run).  Returns a dict with
+        'u', 'v' (lists of planes, if flows), 'matches' (per pair px,py,qx,qy,w, if npoints >= 0),
+        'stats' (per pair), 'ms' (CUDA-event time of the whole stack).  slice_ptrs/out_u/out_v let
+        the caller pass pinned host memory (bench.py); otherwise NumPy arrays are used."""
+        if slice_ptrs is None:
+            slices = [np.ascontiguousarray(s, np.uint8) for s in slices]
+            h, w = slices[0].shape
+            slice_ptrs = [s.ctypes.data for s in slices]
+            pitch = w
+        else:
+            h, w = shape
+        n = len(slice_ptrs)
+        npairs = n - 1
+        io = StackIO()
+        arr = (C.c_void_p * n)(*slice_ptrs)
+        io.h_slices = arr
+        io.pitch = pitch
+        io.n_slices, io.width, io.height = n, w, h
+        io.apply_mask = int(bool(apply_mask))
+        us = vs = None
+        if flows:
+            if out_u is None:
+                us = [np.empty((h, w), np.float32) for _ in range(npairs)]
+                vs = [np.empty((h, w), np.float32) for _ in range(npairs)]
+                out_u = [a.ctypes.data for a in us]
+                out_v = [a.ctypes.data for a in vs]
+            au = (C.c_void_p * npairs)(*out_u)
+            av = (C.c_void_p * npairs)(*out_v)
+            io.h_u, io.h_v = au, av
+            io.pitch_out = w * 4
+        io.npoints = int(npoints)
+        io.scale = float(scale)
+        io.seed = int(seed)
+        cap = max(int(npoints), 1)
+        if npoints >= 0:
+            m = [np.zeros(npairs * cap, np.float64) for _ in range(5)]
+            nout = np.zeros(npairs, np.int32)
+            io.px, io.py, io.qx, io.qy, io.w = (a.ctypes.data for a in m)
+            io.n_out = nout.ctypes.data
+        stats = (Stats * npairs)()
+        io.stats = stats
+        ms = C.c_float(0)
+        check(lib().tvl1_stack_run(self.handle, C.byref(io), C.byref(ms)))
+        res = {"ms": ms.value, "stats": list(stats)}
+        if flows:
+            res["u"], res["v"] = us, vs
+        if npoints >= 0:
+            res["matches"] = [tuple(a[k * cap: k * cap + int(nout[k])] for a in m) for k in range(npairs)]
+        return res
 
     def sample_matches(self, f0, f1, u, v, **kw):
         """Host arrays in, match arrays out (uploads the four planes)."""

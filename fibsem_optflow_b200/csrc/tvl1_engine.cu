@@ -224,6 +224,13 @@ struct tvl1_handle {
     size_t ev_used = 0;
     // sampler scratch (tvl1_sampler.cu)
     void* samp = nullptr;
+    // stack runner (tvl1_stack_run): 3 slice slots, 2 flow buffers, copy streams
+    uint8_t* st_slice[3] = {nullptr, nullptr, nullptr};
+    float* st_flow[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+    size_t st_pitch8 = 0;
+    int st_w = 0, st_h = 0;
+    cudaStream_t st_in = nullptr, st_out = nullptr;
+    cudaEvent_t st_up[3] = {nullptr, nullptr, nullptr}, st_ready[2] = {nullptr, nullptr}, st_down[2] = {nullptr, nullptr};
 };
 
 namespace tvl1 {
@@ -564,6 +571,14 @@ void tvl1_destroy(tvl1_handle* H)
     if (H->d_uo) cudaFree(H->d_uo);
     if (H->d_vo) cudaFree(H->d_vo);
     tvl1::sampler_release(H->samp);
+    for (int i = 0; i < 3; i++) { if (H->st_slice[i]) cudaFree(H->st_slice[i]); if (H->st_up[i]) cudaEventDestroy(H->st_up[i]); }
+    for (int i = 0; i < 2; i++) {
+        for (int j = 0; j < 2; j++) if (H->st_flow[i][j]) cudaFree(H->st_flow[i][j]);
+        if (H->st_ready[i]) cudaEventDestroy(H->st_ready[i]);
+        if (H->st_down[i]) cudaEventDestroy(H->st_down[i]);
+    }
+    if (H->st_in) cudaStreamDestroy(H->st_in);
+    if (H->st_out) cudaStreamDestroy(H->st_out);
     for (cudaEvent_t e : H->events) cudaEventDestroy(e);
     if (H->own_stream) cudaStreamDestroy(H->own_stream);
     delete H;
@@ -636,6 +651,108 @@ int tvl1_mask_flow_u8(tvl1_handle* H, const uint8_t* d_frame1, size_t pitch1, in
     dim3 b(32, 8);
     k_mask_flow<<<grid2d(width, height, b), b, 0, (cudaStream_t)stream>>>(d_frame1, pitch1, width, height, d_u, d_v, pitch_out / 4);
     CK(cudaGetLastError());
+    return TVL1_OK;
+}
+
+// ---- stack of adjacent slices
+
+static int stack_reserve(tvl1_handle* H, int w, int h)
+{
+    if (!H->st_in) {
+        CK(cudaStreamCreateWithFlags(&H->st_in, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&H->st_out, cudaStreamNonBlocking));
+        for (int i = 0; i < 3; i++) CK(cudaEventCreateWithFlags(&H->st_up[i], cudaEventDisableTiming));
+        for (int i = 0; i < 2; i++) {
+            CK(cudaEventCreateWithFlags(&H->st_ready[i], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&H->st_down[i], cudaEventDisableTiming));
+        }
+    }
+    if (H->st_w == w && H->st_h == h) return TVL1_OK;
+    for (int i = 0; i < 3; i++) { if (H->st_slice[i]) cudaFree(H->st_slice[i]); H->st_slice[i] = nullptr; }
+    for (int i = 0; i < 2; i++)
+        for (int j = 0; j < 2; j++) { if (H->st_flow[i][j]) cudaFree(H->st_flow[i][j]); H->st_flow[i][j] = nullptr; }
+    H->st_w = H->st_h = 0;
+    H->st_pitch8 = (size_t)round_up(w, 128);
+    for (int i = 0; i < 3; i++) CK(cudaMalloc(&H->st_slice[i], H->st_pitch8 * h));
+    for (int i = 0; i < 2; i++)
+        for (int j = 0; j < 2; j++) CK(cudaMalloc(&H->st_flow[i][j], (size_t)w * h * sizeof(float)));
+    H->st_w = w; H->st_h = h;
+    return TVL1_OK;
+}
+
+int tvl1_stack_run(tvl1_handle* H, const tvl1_stack_io* io, float* ms_total)
+{
+    if (!H || !io) return fail(TVL1_ERR_INVALID, "null handle or io");
+    const int w = io->width, h = io->height, n = io->n_slices;
+    if (!io->h_slices || n < 2 || w <= 0 || h <= 0 || io->pitch < (size_t)w)
+        return fail(TVL1_ERR_INVALID, "a stack needs >= 2 slices of non-zero size");
+    if ((io->h_u == nullptr) != (io->h_v == nullptr)) return fail(TVL1_ERR_INVALID, "h_u and h_v go together");
+    if (io->h_u && io->pitch_out < (size_t)w * 4) return fail(TVL1_ERR_INVALID, "pitch_out smaller than a row");
+    if (io->npoints >= 0 && (!io->px || !io->py || !io->qx || !io->qy || !io->w || !io->n_out))
+        return fail(TVL1_ERR_INVALID, "match output arrays missing");
+    for (int k = 0; k < n; k++) if (!io->h_slices[k]) return fail(TVL1_ERR_INVALID, "slice %d is null", k);
+    CK(cudaSetDevice(H->device));
+    int rc = stack_reserve(H, w, h);
+    if (rc) return rc;
+    cudaStream_t cs = H->own_stream;
+    const size_t p8 = H->st_pitch8;
+    const int cap = io->npoints > 0 ? io->npoints : 1;
+    cudaEvent_t t0, t1;
+    CK(cudaEventCreate(&t0));
+    CK(cudaEventCreate(&t1));
+    CK(cudaEventRecord(t0, cs));
+    auto upload = [&](int k) -> int {
+        const int s = k % 3;
+        CK(cudaMemcpy2DAsync(H->st_slice[s], p8, io->h_slices[k], io->pitch, w, h, cudaMemcpyHostToDevice, H->st_in));
+        CK(cudaEventRecord(H->st_up[s], H->st_in));
+        return TVL1_OK;
+    };
+    if ((rc = upload(0)) || (rc = upload(1))) return rc;
+    long long rand_skip = 0;
+    for (int k = 0; k + 1 < n; k++) {
+        const int s0 = k % 3, s1 = (k + 1) % 3, fb = k & 1;
+        // slice k+2 goes into the slot pair k-1 read its first frame from; that solve has completed
+        if (k + 2 < n && (rc = upload(k + 2))) return rc;
+        CK(cudaStreamWaitEvent(cs, H->st_up[s0], 0));
+        CK(cudaStreamWaitEvent(cs, H->st_up[s1], 0));
+        if (k >= 2 && io->h_u) CK(cudaStreamWaitEvent(cs, H->st_down[fb], 0));   // flow buffer still draining
+        float* du = H->st_flow[fb][0];
+        float* dv = H->st_flow[fb][1];
+        rc = calc_device(H, H->st_slice[s0], p8, H->st_slice[s1], p8, w, h, du, dv, (size_t)w * 4, cs,
+                         io->stats ? &io->stats[k] : nullptr);
+        if (rc) return rc;
+        if (io->apply_mask) {
+            dim3 b(32, 8);
+            k_mask_flow<<<grid2d(w, h, b), b, 0, cs>>>(H->st_slice[s1], p8, w, h, du, dv, (size_t)w);
+            CK(cudaGetLastError());
+        }
+        if (io->npoints >= 0) {
+            long long used = 0;
+            const size_t o = (size_t)k * cap;
+            rc = tvl1_sample_matches_skip(H, H->st_slice[s0], p8, H->st_slice[s1], p8, du, dv, (size_t)w * 4, w, h,
+                                          0, 0, 0, 0, io->scale, io->npoints, io->seed, io->seed < 0 ? rand_skip : 0,
+                                          io->px + o, io->py + o, io->qx + o, io->qy + o, io->w + o, nullptr,
+                                          &io->n_out[k], &used, cs);
+            if (rc) return rc;
+            rand_skip += used;
+        }
+        if (io->h_u) {
+            CK(cudaEventRecord(H->st_ready[fb], cs));
+            CK(cudaStreamWaitEvent(H->st_out, H->st_ready[fb], 0));
+            CK(cudaMemcpy2DAsync(io->h_u[k], io->pitch_out, du, (size_t)w * 4, (size_t)w * 4, h, cudaMemcpyDeviceToHost, H->st_out));
+            CK(cudaMemcpy2DAsync(io->h_v[k], io->pitch_out, dv, (size_t)w * 4, (size_t)w * 4, h, cudaMemcpyDeviceToHost, H->st_out));
+            CK(cudaEventRecord(H->st_down[fb], H->st_out));
+        }
+    }
+    CK(cudaStreamSynchronize(H->st_out));
+    CK(cudaStreamSynchronize(H->st_in));
+    CK(cudaEventRecord(t1, cs));
+    CK(cudaEventSynchronize(t1));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, t0, t1);
+    if (ms_total) *ms_total = ms;
+    cudaEventDestroy(t0);
+    cudaEventDestroy(t1);
     return TVL1_OK;
 }
 

@@ -110,9 +110,14 @@ __host__ __device__ static inline void window_apply(const uint32_t* c, uint32_t*
     }
 }
 
-static void make_plan(long long seed, RandPlan* plan)
+static void make_plan(long long seed, long long skip, RandPlan* plan)
 {
     glibc_seed_window(seed, plan->base);
+    if (skip > 0) {   // rand() calls already consumed since srand (the reference's debug mode never reseeds)
+        Poly p;
+        poly_xpow((unsigned long long)skip, &p);
+        window_apply(p.c, plan->base);
+    }
     poly_xpow((unsigned long long)RCHUNK, &plan->pw[0]);
     for (int b = 1; b < RBITS; b++) poly_mul(plan->pw[b - 1], plan->pw[b - 1], &plan->pw[b]);
 }
@@ -360,6 +365,19 @@ int tvl1_sample_matches(tvl1_handle* H, const uint8_t* d_frame0, size_t pitch0, 
                         long long seed, double* px, double* py, double* qx, double* qy, double* wgt,
                         int* positions, int* n_out, void* stream)
 {
+    return tvl1_sample_matches_skip(H, d_frame0, pitch0, d_frame1, pitch1, d_u, d_v, pitch_flow, width, height,
+                                    roi0_x, roi0_y, roi1_x, roi1_y, scale, npoints, seed, 0, px, py, qx, qy, wgt,
+                                    positions, n_out, nullptr, stream);
+}
+
+int tvl1_sample_matches_skip(tvl1_handle* H, const uint8_t* d_frame0, size_t pitch0, const uint8_t* d_frame1,
+                             size_t pitch1, const float* d_u, const float* d_v, size_t pitch_flow, int width,
+                             int height, int roi0_x, int roi0_y, int roi1_x, int roi1_y, float scale, int npoints,
+                             long long seed, long long rand_skip, double* px, double* py, double* qx, double* qy,
+                             double* wgt, int* positions, int* n_out, long long* rand_used, void* stream)
+{
+    if (rand_used) *rand_used = 0;
+    if (rand_skip < 0) return fail(TVL1_ERR_INVALID, "rand_skip must be >= 0");
     if (!H) return fail(TVL1_ERR_INVALID, "handle is null");
     if (!d_frame0 || !d_frame1 || !d_u || !d_v || !px || !py || !qx || !qy || !wgt || !n_out)
         return fail(TVL1_ERR_INVALID, "null pointer");
@@ -385,6 +403,7 @@ int tvl1_sample_matches(tvl1_handle* H, const uint8_t* d_frame0, size_t pitch0, 
     std::vector<long long> prefix((size_t)height + 1, 0);
     for (int y = 0; y < height; y++) prefix[(size_t)y + 1] = prefix[(size_t)y] + S->h_rowcount[y];
     const long long N = prefix[(size_t)height];
+    if (rand_used) *rand_used = N > 0 ? N - 1 : 0;   // random_shuffle makes N-1 rand() calls
     if (N == 0) {
         // dummy point so that the fields are present (src/optflow.cpp:560-569)
         px[0] = py[0] = qx[0] = qy[0] = -1.0;
@@ -398,7 +417,7 @@ int tvl1_sample_matches(tvl1_handle* H, const uint8_t* d_frame0, size_t pitch0, 
 
     // 2. search the rand() stream for the steps that decide positions 0..K-1
     RandPlan plan;
-    make_plan(seed, &plan);
+    make_plan(seed, rand_skip, &plan);
     CKS(cudaMemcpyAsync(S->d_plan, &plan, sizeof(plan), cudaMemcpyHostToDevice, st));
     CKS(cudaMemsetAsync(S->d_hit, 0xff, sizeof(int) * (size_t)K, st));   // -1
     CKS(cudaMemsetAsync(S->d_jsmall, 0, sizeof(int) * (size_t)K, st));

@@ -128,6 +128,42 @@ int tvl1_sample_matches(tvl1_handle* h, const uint8_t* d_frame0, size_t pitch0,
                         double* px, double* py, double* qx, double* qy, double* w,
                         int* positions, int* n_out, void* stream);
 
+/* Same, for a process that keeps drawing from one rand() stream (the reference's debug mode
+ * never calls srand, so pair k starts where pair k-1 stopped): rand_skip = rand() calls already
+ * made since the (implicit) srand(seed); *rand_used (may be NULL) receives the calls this
+ * shuffle makes (mask pixels - 1). */
+int tvl1_sample_matches_skip(tvl1_handle* h, const uint8_t* d_frame0, size_t pitch0,
+                             const uint8_t* d_frame1, size_t pitch1,
+                             const float* d_u, const float* d_v, size_t pitch_flow,
+                             int width, int height, int roi0_x, int roi0_y, int roi1_x, int roi1_y,
+                             float scale, int npoints, long long seed, long long rand_skip,
+                             double* px, double* py, double* qx, double* qy, double* w,
+                             int* positions, int* n_out, long long* rand_used, void* stream);
+
+/* A stack of adjacent slices: pairs (k, k+1), k = 0 .. n_slices-2, solved in order on one GPU
+ * (the pair loop of from_file, src/optflow.cpp:86-176, incl. its re-use of the previous pair's
+ * q frame as the next p, :97-103).  Every slice is uploaded once; the upload of slice k+2 and
+ * the download of pair k-1's result run on copy streams while pair k is being solved, so host
+ * buffers should be pinned.  Multi-GPU jobs give each rank a contiguous block of the stack. */
+typedef struct tvl1_stack_io {
+    const uint8_t* const* h_slices;   /* n_slices host pointers, 8-bit rows with byte pitch */
+    size_t pitch;
+    int n_slices, width, height;
+    int apply_mask;                   /* flow = 0 where slice k+1 <= 1 (src/optflow.cpp:471-473) */
+    float* const* h_u;                /* n_slices-1 host planes each, or NULL: no flow download */
+    float* const* h_v;
+    size_t pitch_out;
+    int npoints;                      /* < 0: no match sampling */
+    float scale;
+    long long seed;                   /* >= 0: srand(seed) before every pair; < 0: one unseeded
+                                         stream across the stack (the reference's debug mode) */
+    double *px, *py, *qx, *qy, *w;    /* [(n_slices-1) * max(npoints,1)], or NULL if npoints < 0 */
+    int* n_out;                       /* [n_slices-1] entries written per pair */
+    tvl1_stats* stats;                /* [n_slices-1] or NULL */
+} tvl1_stack_io;
+
+int tvl1_stack_run(tvl1_handle* h, const tvl1_stack_io* io, float* ms_total);
+
 /* ---- stage-level entry points: the individual kernels, exposed so that each can be
  * checked against the oracle on its own (tests/) and profiled on its own (bench.py).
  * Planes are fp32 with a pitch in ELEMENTS; pointers are device memory. ---- */

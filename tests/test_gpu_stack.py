@@ -1,0 +1,58 @@
+"""Stack of adjacent slices through tvl1_stack_run (pipelined uploads/downloads, slice re-use)
+against per-pair oracle solves; debug-mode sampling continues one rand() stream across pairs."""
+import numpy as np
+import pytest
+
+from fibsem_optflow_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def test_stack_flows_and_matches(gpu, orc):
+    slices = synth.make_stack(5, 96, 128, seed=11)        # 6 slices -> 5 pairs
+    slices[2][:8, :] = 0                                  # a masked strip in one slice
+    s = gpu.Solver(gpu.default_params(lambda_=0.15, nscales=4))
+    res = s.run_stack(slices, flows=True, apply_mask=True, npoints=12, scale=0.5, seed=77)
+    assert len(res["u"]) == 5
+    for k in range(5):
+        ou, ov, oit, lev = orc.tvl1_calc(slices[k], slices[k + 1], **{"lambda": 0.15, "nscales": 4})
+        orc.mask_flow(slices[k + 1], ou, ov)
+        assert np.array_equal(res["stats"][k].iters_array(), oit[:lev])
+        assert np.array_equal(res["u"][k], ou) and np.array_equal(res["v"][k], ov)
+        want = orc.random_points(slices[k], slices[k + 1], ou, ov, scale=0.5, npoints=12, seed=77)
+        got = res["matches"][k]
+        for j in range(5):
+            assert np.array_equal(got[j], want[j])
+
+
+def test_stack_debug_stream_continues(gpu, orc):
+    """seed < 0: the reference's debug mode never calls srand, so pair k's shuffle starts where
+    pair k-1's stopped.  The oracle reproduces that with real glibc rand() in a fresh process."""
+    import json, os, subprocess, sys
+    slices = synth.make_stack(3, 40, 56, seed=5)
+    s = gpu.Solver(gpu.default_params(lambda_=0.15, nscales=2))
+    res = s.run_stack(slices, flows=True, npoints=6, scale=1.0, seed=-1)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    np.savez("/tmp/_stack_dbg.npz", slices=np.stack(slices), u=np.stack(res["u"]), v=np.stack(res["v"]))
+    code = (
+        "import sys, json; sys.path.insert(0, %r)\n"
+        "import numpy as np\n"
+        "from oracle import oracle as O\n"
+        "d = np.load('/tmp/_stack_dbg.npz'); out = []\n"
+        "for k in range(3):\n"
+        "    r = O.random_points(d['slices'][k], d['slices'][k+1], d['u'][k], d['v'][k], scale=1.0, npoints=6, seed=-1)\n"
+        "    out.append([a.tolist() for a in r[:5]])\n"
+        "print(json.dumps(out))\n" % root)
+    want = json.loads(subprocess.check_output([sys.executable, "-c", code]).decode())
+    for k in range(3):
+        for j in range(5):
+            assert res["matches"][k][j].tolist() == want[k][j]
+
+
+def test_stack_no_flow_download(gpu):
+    slices = synth.make_stack(2, 64, 64, seed=3)
+    s = gpu.Solver(gpu.default_params(lambda_=0.15, nscales=2))
+    res = s.run_stack(slices, flows=False, npoints=25, seed=1)
+    assert "u" not in res and len(res["matches"]) == 2 and len(res["matches"][0][0]) == 25
+    with pytest.raises(gpu.Tvl1Error):
+        s.run_stack(slices[:1])
