@@ -289,6 +289,34 @@ def run_ours(args):
     clocks = sampler.stop()
     checksum = float(hu[::257, ::263].double().sum() + hv[::257, ::263].double().sum())
 
+    # BASELINE configs[2] excerpt: a stack of chained 4096^2 slices per GPU through
+    # tvl1_stack_run (every slice uploaded once, uploads/downloads overlapped with the solves)
+    stack = None
+    if args.stack_pairs > 0:
+        SS = args.stack_size
+        sl = synth.make_stack(args.stack_pairs, SS, SS, seed=100 + rank)
+        hs = [torch.from_numpy(a).pin_memory() for a in sl]
+        ou = [torch.empty((SS, SS), dtype=torch.float32).pin_memory() for _ in range(args.stack_pairs)]
+        ov = [torch.empty((SS, SS), dtype=torch.float32).pin_memory() for _ in range(args.stack_pairs)]
+        st_solver = N.Solver(N.default_params(lambda_=0.15, nscales=5, warps=5, inner_iterations=30,
+                                              outer_iterations=10), device=local)
+        kw = dict(slices=None, flows=True, apply_mask=True, npoints=25, scale=0.5, seed=1,
+                  out_u=[t.data_ptr() for t in ou], out_v=[t.data_ptr() for t in ov],
+                  slice_ptrs=[t.data_ptr() for t in hs], pitch=SS, shape=(SS, SS))
+        st_solver.run_stack(**kw)
+        barrier()
+        t0 = time.perf_counter()
+        r = st_solver.run_stack(**kw)
+        barrier()
+        ms_stack = allmax((time.perf_counter() - t0) * 1e3)
+        px_stack = allsum(float(SS) * SS * args.stack_pairs)
+        stack = {"workload": "configs[2] excerpt: %d chained %dx%d pairs per GPU, 5 scales, 5 warps, "
+                             "mask + 25 matches + flow download per pair" % (args.stack_pairs, SS, SS),
+                 "value": px_stack / (ms_stack * 1e-3) / 1e6, "unit": UNIT, "ms_per_pair": ms_stack / args.stack_pairs,
+                 "api": "tvl1_stack_run (pinned host buffers, copy streams)",
+                 "iterations_per_pair": [int(x.total_iterations) for x in r["stats"]]}
+        st_solver.close()
+
     px_all = allsum(float(S) * S * K)
     total_launches = int(allsum(float(launches)))
     if rank == 0:
@@ -333,6 +361,8 @@ def run_ours(args):
                                    "warp": stats.ms_warp, "iterate": stats.ms_iterate,
                                    "median": stats.ms_median, "other": stats.ms_other},
         }
+        if stack is not None:
+            line["stack"] = stack
         if world == 1 and not args.no_cpu:
             cb = cpu_leg(args, 1, 0)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
@@ -354,6 +384,8 @@ def main():
     ap.add_argument("--scales", type=int, default=6)
     ap.add_argument("--warps", type=int, default=5)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--stack-pairs", type=int, default=6, help="extra leg: pairs per GPU of the stack excerpt (0 = off)")
+    ap.add_argument("--stack-size", type=int, default=4096)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
