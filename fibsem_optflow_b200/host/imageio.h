@@ -1,0 +1,288 @@
+// imageio.h -- the image I/O the job driver needs, without OpenCV / libpng / libtiff.
+//
+// Stands in for cv::imread(..., IMREAD_GRAYSCALE) (reference src/optflow.cpp:106,119), the
+// optional prescale cv::resize(frame, Size(), scale, scale) (:113,125) and the float
+// cv::imwrite of the flow planes (:478-484).  Readers: PNG (8/16-bit grey, grey+alpha, RGB(A),
+// palette; non-interlaced) through zlib, binary PGM (P5) and uncompressed 8-bit grey baseline
+// TIFF.  Writer: uncompressed 32-bit float single-strip TIFF, which is what
+// support_scripts/upload_matches.py opens with PIL (upload_matches.py:34-37).
+#pragma once
+#include <zlib.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace imio {
+
+struct Gray8 {
+    int w = 0, h = 0;
+    std::vector<uint8_t> px;   // tight rows
+};
+
+inline bool read_file(const std::string& path, std::vector<uint8_t>& out)
+{
+    FILE* f = std::fopen(path.c_str(), "rb");
+    if (!f) return false;
+    std::fseek(f, 0, SEEK_END);
+    const long n = std::ftell(f);
+    std::fseek(f, 0, SEEK_SET);
+    out.resize(n > 0 ? (size_t)n : 0);
+    const size_t got = n > 0 ? std::fread(out.data(), 1, (size_t)n, f) : 0;
+    std::fclose(f);
+    return got == out.size();
+}
+
+// ---- PNG -----------------------------------------------------------------------------------
+
+inline uint32_t be32(const uint8_t* p) { return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]; }
+
+inline uint8_t rgb_to_gray(int r, int g, int b)
+{
+    // libpng png_set_rgb_to_gray(0.299, 0.587), the conversion OpenCV's PNG reader asks for:
+    // 15-bit fixed point, coefficients 9798 / 19235 / 3735
+    return (uint8_t)((9798 * r + 19235 * g + 3735 * b + 16384) >> 15);
+}
+
+inline bool decode_png(const std::vector<uint8_t>& f, Gray8& img, std::string& err)
+{
+    static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
+    if (f.size() < 33 || std::memcmp(f.data(), sig, 8) != 0) { err = "not a PNG"; return false; }
+    size_t p = 8;
+    int w = 0, h = 0, depth = 0, ctype = 0, interlace = 0;
+    std::vector<uint8_t> idat, plte;
+    while (p + 12 <= f.size()) {
+        const uint32_t len = be32(&f[p]);
+        const char* tag = (const char*)&f[p + 4];
+        if (p + 12 + len > f.size()) { err = "truncated PNG chunk"; return false; }
+        const uint8_t* d = &f[p + 8];
+        if (!std::memcmp(tag, "IHDR", 4)) {
+            w = (int)be32(d); h = (int)be32(d + 4); depth = d[8]; ctype = d[9]; interlace = d[12];
+        } else if (!std::memcmp(tag, "PLTE", 4)) {
+            plte.assign(d, d + len);
+        } else if (!std::memcmp(tag, "IDAT", 4)) {
+            idat.insert(idat.end(), d, d + len);
+        } else if (!std::memcmp(tag, "IEND", 4)) {
+            break;
+        }
+        p += 12 + len;
+    }
+    if (w <= 0 || h <= 0) { err = "PNG without IHDR"; return false; }
+    if (interlace) { err = "interlaced PNG is not supported"; return false; }
+    int channels;
+    switch (ctype) {
+        case 0: channels = 1; break;
+        case 2: channels = 3; break;
+        case 3: channels = 1; break;
+        case 4: channels = 2; break;
+        case 6: channels = 4; break;
+        default: err = "bad PNG colour type"; return false;
+    }
+    if (!(depth == 8 || depth == 16 || (depth < 8 && (ctype == 0 || ctype == 3)))) { err = "unsupported PNG bit depth"; return false; }
+    const size_t bpp_bits = (size_t)channels * depth;
+    const size_t stride = ((size_t)w * bpp_bits + 7) / 8;
+    const size_t bpp = bpp_bits >= 8 ? bpp_bits / 8 : 1;
+    std::vector<uint8_t> raw((stride + 1) * (size_t)h);
+    uLongf rawlen = (uLongf)raw.size();
+    if (uncompress(raw.data(), &rawlen, idat.data(), (uLong)idat.size()) != Z_OK || rawlen != raw.size()) {
+        err = "PNG inflate failed";
+        return false;
+    }
+    // unfilter in place
+    std::vector<uint8_t> prev(stride, 0);
+    for (int y = 0; y < h; y++) {
+        uint8_t* row = &raw[(stride + 1) * (size_t)y];
+        const int ft = row[0];
+        uint8_t* c = row + 1;
+        for (size_t i = 0; i < stride; i++) {
+            const int a = i >= bpp ? c[i - bpp] : 0, b = prev[i], cc = i >= bpp ? prev[i - bpp] : 0;
+            int v = c[i];
+            switch (ft) {
+                case 0: break;
+                case 1: v += a; break;
+                case 2: v += b; break;
+                case 3: v += (a + b) >> 1; break;
+                case 4: {
+                    const int pa = std::abs(b - cc), pb = std::abs(a - cc), pc = std::abs(a + b - 2 * cc);
+                    v += (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : cc);
+                    break;
+                }
+                default: err = "bad PNG filter"; return false;
+            }
+            c[i] = (uint8_t)v;
+        }
+        std::memcpy(prev.data(), c, stride);
+    }
+    img.w = w; img.h = h;
+    img.px.resize((size_t)w * h);
+    for (int y = 0; y < h; y++) {
+        const uint8_t* c = &raw[(stride + 1) * (size_t)y + 1];
+        uint8_t* o = &img.px[(size_t)y * w];
+        for (int x = 0; x < w; x++) {
+            if (ctype == 0 || ctype == 4) {
+                if (depth == 8) o[x] = c[(size_t)x * channels];
+                else if (depth == 16) o[x] = c[(size_t)x * channels * 2];   // high byte, like libpng's strip_16
+                else {
+                    const int per = 8 / depth, sh = (per - 1 - x % per) * depth;
+                    const int v = (c[x / per] >> sh) & ((1 << depth) - 1);
+                    o[x] = (uint8_t)(v * 255 / ((1 << depth) - 1));
+                }
+            } else if (ctype == 3) {
+                int idx;
+                if (depth == 8) idx = c[x];
+                else { const int per = 8 / depth, sh = (per - 1 - x % per) * depth; idx = (c[x / per] >> sh) & ((1 << depth) - 1); }
+                if ((size_t)idx * 3 + 2 >= plte.size()) { err = "PNG palette index out of range"; return false; }
+                o[x] = rgb_to_gray(plte[idx * 3], plte[idx * 3 + 1], plte[idx * 3 + 2]);
+            } else {
+                const size_t step = depth == 16 ? 2 : 1;
+                const uint8_t* q = c + (size_t)x * channels * step;
+                o[x] = rgb_to_gray(q[0], q[step], q[2 * step]);
+            }
+        }
+    }
+    return true;
+}
+
+// ---- PGM -----------------------------------------------------------------------------------
+
+inline bool decode_pgm(const std::vector<uint8_t>& f, Gray8& img, std::string& err)
+{
+    size_t p = 2;
+    auto token = [&]() -> long {
+        for (;;) {
+            while (p < f.size() && isspace(f[p])) p++;
+            if (p < f.size() && f[p] == '#') { while (p < f.size() && f[p] != '\n') p++; continue; }
+            break;
+        }
+        long v = 0;
+        bool any = false;
+        while (p < f.size() && isdigit(f[p])) { v = v * 10 + (f[p++] - '0'); any = true; }
+        return any ? v : -1;
+    };
+    const long w = token(), h = token(), mx = token();
+    if (w <= 0 || h <= 0 || mx <= 0 || mx > 255) { err = "unsupported PGM header"; return false; }
+    p++;   // single whitespace after maxval
+    if (p + (size_t)w * h > f.size()) { err = "truncated PGM"; return false; }
+    img.w = (int)w; img.h = (int)h;
+    img.px.assign(f.begin() + p, f.begin() + p + (size_t)w * h);
+    return true;
+}
+
+// ---- TIFF (baseline, uncompressed) -----------------------------------------------------------
+
+inline bool decode_tiff(const std::vector<uint8_t>& f, Gray8& img, std::string& err)
+{
+    if (f.size() < 8) { err = "truncated TIFF"; return false; }
+    const bool le = f[0] == 'I';
+    auto u16 = [&](size_t o) -> uint32_t { return le ? (f[o] | (f[o + 1] << 8)) : ((f[o] << 8) | f[o + 1]); };
+    auto u32 = [&](size_t o) -> uint32_t {
+        return le ? (f[o] | (f[o + 1] << 8) | (f[o + 2] << 16) | ((uint32_t)f[o + 3] << 24))
+                  : (((uint32_t)f[o] << 24) | (f[o + 1] << 16) | (f[o + 2] << 8) | f[o + 3]);
+    };
+    if (u16(2) != 42) { err = "not a TIFF"; return false; }
+    size_t ifd = u32(4);
+    if (ifd + 2 > f.size()) { err = "bad TIFF IFD"; return false; }
+    const uint32_t n = u16(ifd);
+    uint32_t w = 0, h = 0, bits = 1, spp = 1, comp = 1, photo = 1, rps = 0xffffffffu;
+    std::vector<uint32_t> offs, counts;
+    for (uint32_t k = 0; k < n; k++) {
+        const size_t e = ifd + 2 + 12 * (size_t)k;
+        if (e + 12 > f.size()) { err = "bad TIFF IFD"; return false; }
+        const uint32_t tag = u16(e), type = u16(e + 2), cnt = u32(e + 4);
+        const size_t esz = type == 3 ? 2 : (type == 4 ? 4 : 1);
+        const size_t vo = cnt * esz <= 4 ? e + 8 : u32(e + 8);
+        auto val = [&](uint32_t i) -> uint32_t { return type == 3 ? u16(vo + 2 * i) : (type == 4 ? u32(vo + 4 * i) : f[vo + i]); };
+        switch (tag) {
+            case 256: w = val(0); break;
+            case 257: h = val(0); break;
+            case 258: bits = val(0); break;
+            case 259: comp = val(0); break;
+            case 262: photo = val(0); break;
+            case 277: spp = val(0); break;
+            case 278: rps = val(0); break;
+            case 273: for (uint32_t i = 0; i < cnt; i++) offs.push_back(val(i)); break;
+            case 279: for (uint32_t i = 0; i < cnt; i++) counts.push_back(val(i)); break;
+            default: break;
+        }
+    }
+    if (!w || !h || bits != 8 || spp != 1 || comp != 1 || offs.empty()) {
+        err = "only uncompressed 8-bit single-channel TIFF is supported";
+        return false;
+    }
+    if (rps > h) rps = h;
+    img.w = (int)w; img.h = (int)h;
+    img.px.resize((size_t)w * h);
+    size_t row = 0;
+    for (size_t s = 0; s < offs.size() && row < h; s++) {
+        const size_t rows = std::min<size_t>(rps, h - row), bytes = rows * w;
+        if (offs[s] + bytes > f.size()) { err = "truncated TIFF strip"; return false; }
+        std::memcpy(&img.px[row * w], &f[offs[s]], bytes);
+        row += rows;
+    }
+    if (photo == 0) for (auto& v : img.px) v = (uint8_t)(255 - v);   // WhiteIsZero
+    return true;
+}
+
+inline bool read_gray8(const std::string& path, Gray8& img, std::string& err)
+{
+    std::vector<uint8_t> f;
+    if (!read_file(path, f) || f.size() < 4) { err = "cannot read " + path; return false; }
+    if (f[0] == 0x89 && f[1] == 'P') return decode_png(f, img, err);
+    if (f[0] == 'P' && f[1] == '5') return decode_pgm(f, img, err);
+    if ((f[0] == 'I' && f[1] == 'I') || (f[0] == 'M' && f[1] == 'M')) return decode_tiff(f, img, err);
+    err = "unknown image format: " + path;
+    return false;
+}
+
+// cv::resize(img, Size(), 0.5, 0.5) on 8-bit data: OpenCV takes its INTER_AREA fast path for an
+// exact 2x decimation, (a+b+c+d+2)>>2.  Even sizes only.
+inline bool half_scale(const Gray8& in, Gray8& out, std::string& err)
+{
+    if ((in.w | in.h) & 1) { err = "scale 0.5 needs even image sizes"; return false; }
+    out.w = in.w / 2; out.h = in.h / 2;
+    out.px.resize((size_t)out.w * out.h);
+    for (int y = 0; y < out.h; y++) {
+        const uint8_t* a = &in.px[(size_t)(2 * y) * in.w];
+        const uint8_t* b = a + in.w;
+        uint8_t* o = &out.px[(size_t)y * out.w];
+        for (int x = 0; x < out.w; x++) o[x] = (uint8_t)((a[2 * x] + a[2 * x + 1] + b[2 * x] + b[2 * x + 1] + 2) >> 2);
+    }
+    return true;
+}
+
+// ---- float TIFF writer -----------------------------------------------------------------------
+
+inline bool write_tiff_f32(const std::string& path, const float* data, int w, int h)
+{
+    FILE* f = std::fopen(path.c_str(), "wb");
+    if (!f) return false;
+    const uint32_t nbytes = (uint32_t)((size_t)w * h * 4);
+    const uint32_t ifd_off = 8 + nbytes;
+    uint8_t hdr[8] = {'I', 'I', 42, 0, 0, 0, 0, 0};
+    std::memcpy(hdr + 4, &ifd_off, 4);
+    std::fwrite(hdr, 1, 8, f);
+    std::fwrite(data, 4, (size_t)w * h, f);
+    struct Entry { uint16_t tag, type; uint32_t count, value; };
+    const Entry e[] = {
+        {256, 4, 1, (uint32_t)w}, {257, 4, 1, (uint32_t)h}, {258, 3, 1, 32}, {259, 3, 1, 1},
+        {262, 3, 1, 1}, {273, 4, 1, 8}, {277, 3, 1, 1}, {278, 4, 1, (uint32_t)h},
+        {279, 4, 1, nbytes}, {339, 3, 1, 3},   // SampleFormat = IEEE float
+    };
+    const uint16_t n = sizeof(e) / sizeof(e[0]);
+    std::fwrite(&n, 2, 1, f);
+    for (const Entry& x : e) {
+        std::fwrite(&x.tag, 2, 1, f);
+        std::fwrite(&x.type, 2, 1, f);
+        std::fwrite(&x.count, 4, 1, f);
+        std::fwrite(&x.value, 4, 1, f);
+    }
+    const uint32_t next = 0;
+    std::fwrite(&next, 4, 1, f);
+    const bool ok = std::ferror(f) == 0;
+    std::fclose(f);
+    return ok;
+}
+
+}  // namespace imio

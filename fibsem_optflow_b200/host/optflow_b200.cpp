@@ -1,0 +1,405 @@
+// optflow_b200 -- job driver: the reference's `optflow <job.json[.gz]>` CLI on top of the C ABI.
+//
+// Mirrors main / from_file / get_rois / solve_rois / solve_wrapper / move_pm / upload_points of
+// the reference (src/optflow.cpp:29-178, 228-261, 302-392, 395-497, 574-641) for the
+// features == false path:
+//   * same job JSON (comments tolerated, .gz transparently inflated), same key precedence
+//     im_args.get(key, args.get(key, default));
+//   * same pair loop incl. re-use of the previous pair's decoded frame (:97-103);
+//   * same ROI keys ("top", "bottom", "custom", "custom" with "0"/"1") walked in jsoncpp's
+//     alphabetical member order; same output naming
+//     <output_dir>/<output_name>_<scale %0.2f>[_top|_bottom]_{x,y}.tiff (:155-157, :345, :480-481);
+//   * output_type "map" | "flow" -> float TIFF planes, "random_points" -> match records.
+// Differences, all because the dependency is out of scope or absent here:
+//   * no ORB/SURF pre-alignment (src/features.cpp): a job that asks for "features", or pairs of
+//     different size, are rejected; a pair without any ROI is solved on the whole frame
+//     without the alignment the reference would force (:366);
+//   * match batches are written to <output_dir>/point_matches_<n>.json with exactly the payload
+//     upload_points would PUT to the Render service (:620-634) -- there is no network here;
+//   * `scale` must be 1 or 0.5 (the two values whose 8-bit cv::resize result is pinned).
+// All arithmetic runs in libtvl1_b200.so; this file only moves bytes and JSON.
+#include <zlib.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <ctime>
+#include <iostream>
+#include <string>
+#include <vector>
+
+#include "../../include/tvl1_b200.h"
+#include "imageio.h"
+#include "minijson.h"
+
+using mj::Value;
+
+namespace {
+
+struct Rect { int x, y, w, h; };
+
+struct DeviceFrame {
+    void* ptr = nullptr;
+    size_t bytes = 0;
+};
+
+struct Driver {
+    int device = 0;
+    tvl1_handle* solver = nullptr;
+    tvl1_params cur{};
+    bool have_params = false;
+    DeviceFrame d0, d1, du, dv;
+    long long rand_skip = 0;   // debug mode: one rand() stream for the whole process
+    int uploads = 0;
+
+    ~Driver()
+    {
+        if (solver) tvl1_destroy(solver);
+        for (DeviceFrame* f : {&d0, &d1, &du, &dv})
+            if (f->ptr) tvl1_dev_free(device, f->ptr);
+    }
+};
+
+[[noreturn]] void die(const std::string& m)
+{
+    std::cerr << "optflow_b200: " << m << "\n";
+    std::exit(2);
+}
+
+void ck(int rc, const char* what)
+{
+    if (rc < 0) die(std::string(what) + ": " + tvl1_last_error());
+}
+
+const Value& pick(const Value& im, const Value& args, const char* key, const Value& dflt)
+{
+    // im_args.get(key, args.get(key, default))
+    return im.get(key, args.get(key, dflt));
+}
+
+std::string slurp(const std::string& path)
+{
+    gzFile g = gzopen(path.c_str(), "rb");   // reads plain files too
+    if (!g) die("cannot open " + path);
+    std::string s;
+    char buf[1 << 16];
+    int n;
+    while ((n = gzread(g, buf, sizeof(buf))) > 0) s.append(buf, (size_t)n);
+    gzclose(g);
+    return s;
+}
+
+void reserve(Driver& D, DeviceFrame& f, size_t bytes)
+{
+    if (f.bytes >= bytes) return;
+    if (f.ptr) tvl1_dev_free(D.device, f.ptr);
+    f.ptr = nullptr;
+    ck(tvl1_dev_alloc(D.device, bytes, &f.ptr), "device allocation");
+    f.bytes = bytes;
+}
+
+// generate_TV_args (src/optflow.cpp:500-514) + the optional CPU-class keys
+tvl1_params tv_params(const Value& im, const Value& args)
+{
+    tvl1_params p;
+    tvl1_default_params(&p);
+    p.tau = pick(im, args, "tau", Value(0.25)).asDouble();
+    p.lambda = pick(im, args, "lambda", Value(0.05)).asDouble();
+    p.theta = pick(im, args, "theta", Value(0.3)).asDouble();
+    p.nscales = (int)pick(im, args, "nscales", Value(10)).asInt();
+    p.warps = (int)pick(im, args, "warps", Value(5)).asInt();
+    p.epsilon = pick(im, args, "epsilon", Value(0.01)).asDouble();
+    p.iterations = (int)pick(im, args, "iterations", Value(300)).asInt();
+    p.scale_step = pick(im, args, "scaleStep", Value(0.8)).asDouble();
+    p.gamma = pick(im, args, "gamma", Value(0.0)).asDouble();
+    p.use_initial_flow = 0;   // read but never forwarded by the reference (:512, :518)
+    p.inner_iterations = (int)pick(im, args, "innerIterations", Value(0)).asInt();
+    p.outer_iterations = (int)pick(im, args, "outerIterations", Value(0)).asInt();
+    p.median_filtering = (int)pick(im, args, "medianFiltering", Value(5)).asInt();
+    return p;
+}
+
+void ensure_solver(Driver& D, const tvl1_params& p)
+{
+    if (!D.solver) {
+        ck(tvl1_create(&p, D.device, &D.solver), "tvl1_create");
+    } else if (!D.have_params || std::memcmp(&p, &D.cur, sizeof(p)) != 0) {
+        ck(tvl1_set_params(D.solver, &p), "tvl1_set_params");
+    }
+    D.cur = p;
+    D.have_params = true;
+}
+
+Rect roi_from_array(const Value& a)
+{
+    if (!a.isArray() || a.size() < 4) die("an roi must be [x, y, width, height]");
+    return Rect{(int)a[0].asInt(), (int)a[1].asInt(), (int)a[2].asInt(), (int)a[3].asInt()};
+}
+
+// get_rois (src/optflow.cpp:228-261)
+void get_rois(Value& rois, const Value& spec, int rows, int cols)
+{
+    auto rect = [](int x, int y, int w, int h) {
+        Value v = Value::array();
+        v.append(Value(x)); v.append(Value(y)); v.append(Value(w)); v.append(Value(h));
+        return v;
+    };
+    if (spec.isMember("top")) rois["top"] = rect(0, 0, cols, (int)spec.get("top", Value(300)).asInt());
+    if (spec.isMember("bottom")) {
+        const int b = (int)spec.get("bottom", Value(300)).asInt();
+        rois["bottom"] = rect(0, rows - b, cols, b);
+    }
+    if (spec.isMember("custom")) {
+        const Value& c = spec.at("custom");
+        if (c.isMember("0")) {
+            if (!c.isMember("1")) die("rois.custom with \"0\" needs \"1\" as well");
+            rois["custom_diff"]["0"] = c.at("0");
+            rois["custom_diff"]["1"] = c.at("1");
+        } else {
+            rois["custom"] = c;
+        }
+    }
+}
+
+void check_roi(const Rect& r, int w, int h, const char* which)
+{
+    if (r.w <= 0 || r.h <= 0 || r.x < 0 || r.y < 0 || r.x + r.w > w || r.y + r.h > h)
+        die(std::string("roi outside the frame (") + which + ")");
+}
+
+// solve_wrapper (src/optflow.cpp:395-497), features == false
+void solve_wrapper(Driver& D, const imio::Gray8& f0, const imio::Gray8& f1, const Rect& r0, const Rect& r1,
+                   Value& im, const Value& args)
+{
+    if (r0.w != r1.w || r0.h != r1.h) die("the two rois of a pair must have the same size");
+    const int w = r0.w, h = r0.h;
+    ensure_solver(D, tv_params(im, args));
+    reserve(D, D.du, (size_t)w * h * 4);
+    reserve(D, D.dv, (size_t)w * h * 4);
+    const uint8_t* p0 = (const uint8_t*)D.d0.ptr + (size_t)r0.y * f0.w + r0.x;   // ROI views: pointer + pitch
+    const uint8_t* p1 = (const uint8_t*)D.d1.ptr + (size_t)r1.y * f1.w + r1.x;
+    ck(tvl1_calc_u8(D.solver, p0, (size_t)f0.w, p1, (size_t)f1.w, w, h, (float*)D.du.ptr, (float*)D.dv.ptr,
+                    (size_t)w * 4, nullptr, nullptr), "tvl1_calc_u8");
+
+    const std::string output_type = pick(im, args, "output_type", Value("map")).asString();
+    if (output_type == "random_points") {
+        ck(tvl1_mask_flow_u8(D.solver, p1, (size_t)f1.w, w, h, (float*)D.du.ptr, (float*)D.dv.ptr, (size_t)w * 4, nullptr),
+           "tvl1_mask_flow_u8");
+        const bool debug = args.get("debug", Value(false)).asBool();
+        const float scale = pick(im, args, "scale", Value(0.5)).asFloat();
+        const int npoints = (int)pick(im, args, "npoints", Value(25)).asInt();
+        const int cap = npoints > 0 ? npoints : 1;
+        std::vector<double> px(cap), py(cap), qx(cap), qy(cap), wt(cap);
+        int n = 0;
+        long long used = 0;
+        // srand(time(0)) unless debug (:532-535); debug keeps drawing from one unseeded stream
+        const long long seed = debug ? -1 : (long long)std::time(nullptr);
+        ck(tvl1_sample_matches_skip(D.solver, p0, (size_t)f0.w, p1, (size_t)f1.w, (float*)D.du.ptr, (float*)D.dv.ptr,
+                                    (size_t)w * 4, w, h, r0.x, r0.y, r1.x, r1.y, scale, npoints, seed,
+                                    debug ? D.rand_skip : 0, px.data(), py.data(), qx.data(), qy.data(), wt.data(),
+                                    nullptr, &n, &used, nullptr), "tvl1_sample_matches");
+        if (debug) D.rand_skip += used;
+        Value& pm = im["point_matches"];
+        if (!pm.isMember("p")) {
+            pm["p"] = Value::array(); pm["p"].append(Value::array()); pm["p"].append(Value::array());
+            pm["q"] = Value::array(); pm["q"].append(Value::array()); pm["q"].append(Value::array());
+            pm["w"] = Value::array();
+        }
+        for (int k = 0; k < n; k++) {
+            pm["w"].append(Value((long long)(wt[k] != 0.0 ? 1 : 0)));
+            pm["p"][0].append(Value(px[k])); pm["p"][1].append(Value(py[k]));
+            pm["q"][0].append(Value(qx[k])); pm["q"][1].append(Value(qy[k]));
+        }
+        return;
+    }
+    // "map" | "flow": planes to the host, coordinate grid (map), mask, float TIFFs
+    std::vector<float> fx((size_t)w * h), fy((size_t)w * h);
+    ck(tvl1_dev_d2h(fx.data(), D.du.ptr, fx.size() * 4), "download");
+    ck(tvl1_dev_d2h(fy.data(), D.dv.ptr, fy.size() * 4), "download");
+    const bool map = output_type == "map";
+    for (int y = 0; y < h; y++) {
+        const uint8_t* m = &f1.px[(size_t)(r1.y + y) * f1.w + r1.x];
+        for (int x = 0; x < w; x++) {
+            const size_t i = (size_t)y * w + x;
+            if (map) { fx[i] = fx[i] + (float)x; fy[i] = fy[i] + (float)y; }   // :451-465
+            if (m[x] <= 1) { fx[i] = 0.f; fy[i] = 0.f; }                       // :471-473
+        }
+    }
+    const std::string base = im.at("output").asString() + im.at("output_suffix").asString();
+    if (!imio::write_tiff_f32(base + "_x.tiff", fx.data(), w, h) || !imio::write_tiff_f32(base + "_y.tiff", fy.data(), w, h))
+        die("cannot write " + base + "_{x,y}.tiff");
+}
+
+// move_pm (src/optflow.cpp:574-593)
+void move_pm(Value& im, Value& args)
+{
+    Value single = Value::object();
+    single["pGroupId"] = im.at("pGroupId");
+    single["pId"] = im.at("pId");
+    single["qGroupId"] = im.at("qGroupId");
+    single["qId"] = im.at("qId");
+    single["matches"] = im.at("point_matches");
+    args["point_matches"].append(single);
+    im["point_matches"] = Value::object();
+}
+
+// upload_points (src/optflow.cpp:595-641): same payload, written to a file instead of PUT
+void upload_points(Driver& D, Value& args)
+{
+    const std::string dir = args.get("output_dir", Value(".")).asString();
+    char name[64];
+    std::snprintf(name, sizeof(name), "/point_matches_%03d.json", D.uploads++);
+    const std::string path = args.get("matches_file", Value(dir + name)).asString();
+    const std::string payload = mj::dump(args.at("point_matches"));
+    FILE* f = std::fopen(path.c_str(), "wb");
+    if (!f) die("cannot write " + path);
+    std::fwrite(payload.data(), 1, payload.size(), f);
+    std::fclose(f);
+    if (args.get("debug", Value(false)).asBool()) {
+        std::cout << payload << "\n";
+        std::cout << "http://" << args.get("host", Value("10.40.3.162")).asString() << ":" << args.get("port", Value("8080")).asString()
+                  << "/render-ws/v1/owner/" << args.get("owner", Value("flyem")).asString() << "/matchCollection/"
+                  << args.get("matchCollection", Value("forgetful_owner")).asString() << "/matches -> " << path << "\n";
+    }
+}
+
+bool load_frame(const std::string& path, float scale, imio::Gray8& out)
+{
+    imio::Gray8 raw;
+    std::string err;
+    if (!imio::read_gray8(path, raw, err)) {
+        std::cout << "Error: " << path << " (" << err << ")\n";
+        return false;
+    }
+    if (scale == 1.f) { out = std::move(raw); return true; }
+    if (scale == 0.5f) {
+        if (!imio::half_scale(raw, out, err)) { std::cout << "Error: " << path << " (" << err << ")\n"; return false; }
+        return true;
+    }
+    die("scale must be 1 or 0.5 (other factors of the 8-bit cv::resize are not restated)");
+}
+
+// solve_rois (src/optflow.cpp:312-392)
+void solve_rois(Driver& D, const imio::Gray8& f0, const imio::Gray8& f1, const Value& rois, Value& im, Value& args)
+{
+    const bool want_features = (im.isMember("features") ? im.at("features").asBool() : args.get("features", Value(false)).asBool());
+    if (want_features) die("\"features\" (ORB/SURF pre-alignment) is not part of this build");
+    reserve(D, D.d0, f0.px.size());
+    reserve(D, D.d1, f1.px.size());
+    ck(tvl1_dev_h2d(D.d0.ptr, f0.px.data(), f0.px.size()), "upload");
+    ck(tvl1_dev_h2d(D.d1.ptr, f1.px.data(), f1.px.size()), "upload");
+    for (const auto& kv : *rois.o) {   // alphabetical, like Json::Value::getMemberNames()
+        const std::string& key = kv.first;
+        im["output_suffix"] = (key == "top" || key == "bottom") ? Value("_" + key) : Value("");
+        if (key == "custom_diff") {
+            const Rect r0 = roi_from_array(kv.second.at("0")), r1 = roi_from_array(kv.second.at("1"));
+            check_roi(r0, f0.w, f0.h, "custom 0");
+            check_roi(r1, f1.w, f1.h, "custom 1");
+            solve_wrapper(D, f0, f1, r0, r1, im, args);
+        } else {
+            if (f0.w != f1.w || f0.h != f1.h) die("frames of different size need the feature pre-alignment, which is not part of this build");
+            if (key == "default")
+                std::cerr << "note: no roi given; the reference would pre-align with features here, this build solves the whole frame as is\n";
+            const Rect r = roi_from_array(kv.second);
+            check_roi(r, f0.w, f0.h, key.c_str());
+            solve_wrapper(D, f0, f1, r, r, im, args);
+        }
+    }
+    if (pick(im, args, "output_type", Value("map")).asString() == "random_points") move_pm(im, args);
+}
+
+// from_file (src/optflow.cpp:75-178)
+int from_file(Driver& D, Value& args, int shard, int nshards)
+{
+    const Value images = args.at("images");
+    if (!images.isArray()) die("\"images\" must be an array");
+    // the reference keeps the previous pair's frames so that a slice shared by adjacent pairs
+    // (q of pair i-1 == p of pair i) is not decoded twice (:97-103); same idea, two cache slots
+    struct Cached { std::string name; float scale = -1.f; imio::Gray8 img; };
+    Cached cache[2];
+    long long last_upload = 0;
+    bool any_upload_since = false;
+    const size_t n = images.size();
+    const size_t base = n / nshards, rem = n % nshards;
+    const size_t begin = shard * base + std::min<size_t>(shard, rem), end = begin + base + ((size_t)shard < rem ? 1 : 0);
+    for (size_t i = begin; i < end; i++) {
+        Value im = images[i];
+        const std::string n0 = im.at("p").asString(), n1 = im.at("q").asString();
+        const float scale = im.get("scale", args.get("scale", Value(0.5))).asFloat();
+        im["scale"] = Value((double)scale);
+        std::cout << n0 << " " << n1 << "\n";
+        imio::Gray8 frame0, frame1;
+        auto fetch = [&](const std::string& name, imio::Gray8& out) -> bool {
+            for (Cached& c : cache)
+                if (c.name == name && c.scale == scale) { out = c.img; return true; }
+            return load_frame(name, scale, out);
+        };
+        if (!fetch(n0, frame0) || !fetch(n1, frame1)) continue;
+        cache[0].name = n0; cache[0].scale = scale; cache[0].img = frame0;
+        cache[1].name = n1; cache[1].scale = scale; cache[1].img = frame1;
+
+        Value rois = Value::object();
+        const int rows = std::min(frame0.h, frame1.h), cols = std::min(frame0.w, frame1.w);
+        if (im.isMember("rois")) get_rois(rois, im.at("rois"), rows, cols);
+        else if (args.isMember("rois")) get_rois(rois, args.at("rois"), rows, cols);
+        if (rois.size() == 0) {
+            Value r = Value::array();
+            r.append(Value(0)); r.append(Value(0)); r.append(Value(cols)); r.append(Value(rows));
+            rois["default"] = r;
+        }
+        char buffer[32];
+        std::snprintf(buffer, sizeof(buffer), "%0.2f", scale);
+        if (!im.isMember("output"))
+            im["output"] = Value(args.at("output_dir").asString() + "/" + im.at("output_name").asString() + "_" + buffer);
+        solve_rois(D, frame0, frame1, rois, im, args);
+
+        if (pick(im, args, "output_type", Value("map")).asString() == "random_points") {
+            any_upload_since = true;
+            if ((long long)i > last_upload + args.get("batch_size", Value(100)).asInt()) {
+                upload_points(D, args);
+                args["point_matches"] = Value::array();
+                last_upload = (long long)i;
+                any_upload_since = false;
+            }
+        }
+    }
+    if (any_upload_since) upload_points(D, args);
+    return 0;
+}
+
+}  // namespace
+
+int main(int argc, const char* argv[])
+{
+    std::string filename;
+    int device = 0, shard = 0, nshards = 1;
+    for (int k = 1; k < argc; k++) {
+        const std::string a = argv[k];
+        if (a == "-h" || a == "--help") {
+            std::cout << "usage: optflow_b200 [--device N] [--shard RANK/WORLD] <job.json[.gz]>\n"
+                         "  --shard: solve only this rank's contiguous block of \"images\" (one process per GPU)\n";
+            return 0;
+        } else if (a == "--device" && k + 1 < argc) {
+            device = std::atoi(argv[++k]);
+        } else if (a == "--shard" && k + 1 < argc) {
+            if (std::sscanf(argv[++k], "%d/%d", &shard, &nshards) != 2 || nshards < 1 || shard < 0 || shard >= nshards)
+                die("--shard wants RANK/WORLD");
+        } else {
+            filename = a;
+        }
+    }
+    if (filename.empty()) die("no job file given (see --help)");
+    Value args;
+    try {
+        args = mj::parse(slurp(filename));
+    } catch (const std::exception& e) {
+        die(std::string(e.what()) + " in " + filename);   // the reference ignores parse errors (:51,56); we do not
+    }
+    if (tvl1_dev_count() <= 0) die("no CUDA device: this driver has no CPU path");
+    const int style = (int)args.get("style", Value(1)).asInt();
+    if (style != 1) die("only \"style\": 1 exists");
+    Driver D;
+    D.device = device;
+    return from_file(D, args, shard, nshards);
+}

@@ -1,0 +1,132 @@
+"""The job driver (fibsem_optflow_b200/host/optflow_b200, N1): same job JSON as the reference CLI,
+outputs checked against the oracle -- float TIFF planes for "flow"/"map", match records for
+"random_points" (debug mode: one unseeded rand() stream over all ROIs and pairs, in the
+reference's alphabetical ROI order)."""
+import gzip
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from fibsem_optflow_b200 import synth
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "fibsem_optflow_b200", "host", "optflow_b200")
+
+
+def build_cli():
+    subprocess.check_call(["make", "-C", os.path.dirname(EXE), "-s"])
+    return EXE
+
+
+def write_png(path, a):
+    import cv2
+    assert cv2.imwrite(path, a)
+
+
+def write_pgm(path, a):
+    with open(path, "wb") as f:
+        f.write(b"P5\n# test\n%d %d\n255\n" % (a.shape[1], a.shape[0]))
+        f.write(a.tobytes())
+
+
+def read_tiff_f32(path):
+    from PIL import Image
+    return np.array(Image.open(path), dtype=np.float32)
+
+
+def test_flow_and_map_tiffs(gpu, orc, tmp_path):
+    exe = build_cli()
+    sl = synth.make_stack(2, 256, 320, seed=21)         # 3 slices, prescaled by 0.5 in the driver
+    sl[1][:16, :] = 0
+    names = []
+    for k, a in enumerate(sl):
+        p = str(tmp_path / ("s%d.%s" % (k, "png" if k != 1 else "pgm")))
+        (write_png if k != 1 else write_pgm)(p, a)
+        names.append(p)
+    job = """{
+      /* a comment, as in docs/example.json */
+      "debug": true, "style": 1, "features": false,
+      "images": [ {"p": "%s", "q": "%s", "output_name": "a~b", "output_type": "flow"},
+                  {"p": "%s", "q": "%s", "output_name": "b~c", "output_type": "map", "nscales": 3}, ],
+      "rois": {"top": 40, "bottom": 48},
+      "lambda": 0.15, "nscales": 4, "scale": 0.5, // trailing comma above is tolerated too
+      "output_dir": "%s"
+    }""" % (names[0], names[1], names[1], names[2], str(tmp_path))
+    jf = str(tmp_path / "job.json.gz")
+    with gzip.open(jf, "wt") as f:
+        f.write(job)
+    subprocess.check_call([exe, jf])
+    half = [((a[0::2, 0::2].astype(np.int32) + a[0::2, 1::2] + a[1::2, 0::2] + a[1::2, 1::2] + 2) >> 2).astype(np.uint8)
+            for a in sl]
+    H, W = half[0].shape
+    for (name, k, nsc, is_map) in (("a~b", 0, 4, False), ("b~c", 1, 3, True)):
+        for key, (y0, hh) in (("top", (0, 40)), ("bottom", (H - 48, 48))):
+            f0, f1 = half[k][y0:y0 + hh], half[k + 1][y0:y0 + hh]
+            ou, ov, _, _ = orc.tvl1_calc(f0, f1, **{"lambda": 0.15, "nscales": nsc})
+            if is_map:
+                ou = ou + np.arange(W, dtype=np.float32)[None, :]
+                ov = ov + np.arange(hh, dtype=np.float32)[:, None]
+            ou = np.where(f1 <= 1, np.float32(0), ou)
+            ov = np.where(f1 <= 1, np.float32(0), ov)
+            base = str(tmp_path / ("%s_0.50_%s" % (name, key)))
+            assert np.array_equal(read_tiff_f32(base + "_x.tiff"), ou), (name, key)
+            assert np.array_equal(read_tiff_f32(base + "_y.tiff"), ov), (name, key)
+
+
+def test_random_points_job(gpu, orc, tmp_path):
+    exe = build_cli()
+    sl = synth.make_stack(2, 96, 128, seed=4)
+    names = []
+    for k, a in enumerate(sl):
+        p = str(tmp_path / ("t%d.png" % k))
+        write_png(p, a)
+        names.append(p)
+    job = {"debug": True, "output_type": "random_points", "scale": 1.0, "lambda": 0.15, "nscales": 3,
+           "npoints": 7, "output_dir": str(tmp_path), "rois": {"top": 32, "bottom": 40},
+           "images": [{"p": names[0], "q": names[1], "pId": "t0", "qId": "t1", "pGroupId": "1.0", "qGroupId": "2.0"},
+                      {"p": names[1], "q": names[2], "pId": "t1", "qId": "t2", "pGroupId": "2.0", "qGroupId": "3.0",
+                       "rois": {"custom": [8, 16, 100, 60]}}]}
+    jf = str(tmp_path / "job.json")
+    json.dump(job, open(jf, "w"))
+    subprocess.check_call([exe, jf], stdout=subprocess.DEVNULL)
+    got = json.load(open(str(tmp_path / "point_matches_000.json")))
+    assert [g["pId"] for g in got] == ["t0", "t1"] and got[1]["qGroupId"] == "3.0"
+    # the same job through the oracle, in a fresh process (unseeded rand() stream), ROI keys in
+    # jsoncpp's alphabetical order: bottom, then top
+    np.savez(str(tmp_path / "in.npz"), sl=np.stack(sl))
+    code = (
+        "import sys, json; sys.path.insert(0, %r)\n"
+        "import numpy as np\n"
+        "from oracle import oracle as O\n"
+        "sl = np.load(%r)['sl']; H, W = sl[0].shape; out = []\n"
+        "jobs = [(0, [(0, H - 40, W, 40), (0, 0, W, 32)]), (1, [(8, 16, 100, 60)])]\n"
+        "for k, rois in jobs:\n"
+        "    rec = [[], [], [], [], []]\n"
+        "    for (x, y, w, h) in rois:\n"
+        "        f0 = np.ascontiguousarray(sl[k][y:y+h, x:x+w]); f1 = np.ascontiguousarray(sl[k+1][y:y+h, x:x+w])\n"
+        "        u, v, _, _ = O.tvl1_calc(f0, f1, **{'lambda': 0.15, 'nscales': 3})\n"
+        "        O.mask_flow(f1, u, v)\n"
+        "        r = O.random_points(f0, f1, u, v, roi0=(x, y), roi1=(x, y), scale=1.0, npoints=7, seed=-1)\n"
+        "        for j in range(5): rec[j] += r[j].tolist()\n"
+        "    out.append(rec)\n"
+        "print(json.dumps(out))\n" % (ROOT, str(tmp_path / "in.npz")))
+    want = json.loads(subprocess.check_output([sys.executable, "-c", code]).decode())
+    for k in range(2):
+        m = got[k]["matches"]
+        assert m["p"][0] == want[k][0] and m["p"][1] == want[k][1]
+        assert m["q"][0] == want[k][2] and m["q"][1] == want[k][3]
+        assert m["w"] == [int(x) for x in want[k][4]]
+
+
+def test_cli_rejects(gpu, tmp_path):
+    exe = build_cli()
+    jf = str(tmp_path / "bad.json")
+    open(jf, "w").write('{"images": [], "features": 1, "style": 2}')
+    assert subprocess.call([exe, jf], stderr=subprocess.DEVNULL) != 0
+    open(jf, "w").write('{"images": [ {"p": "x" "q": "y"} ]}')     # missing comma, like docs/example.json:72
+    assert subprocess.call([exe, jf], stderr=subprocess.DEVNULL) != 0
