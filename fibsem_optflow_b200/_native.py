@@ -70,9 +70,9 @@ class StackIO(C.Structure):
 # every symbol include/tvl1_b200.h declares (checked by tests/test_abi.py)
 EXPORTS = [
     "tvl1_version", "tvl1_last_error", "tvl1_default_params", "tvl1_create", "tvl1_destroy",
-    "tvl1_set_params", "tvl1_set_timing", "tvl1_calc_u8", "tvl1_calc_u8_host",
+    "tvl1_set_params", "tvl1_set_option", "tvl1_set_timing", "tvl1_calc_u8", "tvl1_calc_u8_host",
     "tvl1_mask_flow_u8", "tvl1_sample_matches", "tvl1_sample_matches_skip", "tvl1_stack_run", "tvl1_k_convert_u8", "tvl1_k_resize",
-    "tvl1_k_centered_gradient", "tvl1_k_warp", "tvl1_k_iterate", "tvl1_k_median5", "tvl1_k_last_ms",
+    "tvl1_k_centered_gradient", "tvl1_k_warp", "tvl1_k_iterate", "tvl1_k_iterate_fused2", "tvl1_k_median5", "tvl1_k_last_ms",
     "tvl1_pyramid_sizes", "tvl1_glibc_rand", "tvl1_selftest_arith", "tvl1_dev_count", "tvl1_dev_alloc", "tvl1_dev_free",
     "tvl1_dev_memset", "tvl1_dev_h2d", "tvl1_dev_d2h", "tvl1_dev_sync",
     "tvl1_host_alloc_pinned", "tvl1_host_free_pinned",
@@ -93,6 +93,13 @@ def lib():
             "%s is missing: build it with `python fibsem_optflow_b200/csrc/build.py` "
             "(there is no CPU fallback)" % SO_PATH)
     L = C.CDLL(SO_PATH)
+    if os.environ.get("TVL1_SO"):
+        # developer A/B builds may predate newer entry points: give them inert placeholders
+        class _Missing:
+            argtypes = restype = None
+        for name in EXPORTS:
+            if not hasattr(L, name):
+                setattr(L, name, _Missing())
     L.tvl1_version.restype = C.c_char_p
     L.tvl1_last_error.restype = C.c_char_p
     L.tvl1_default_params.argtypes = [C.POINTER(Params)]
@@ -102,6 +109,7 @@ def lib():
     L.tvl1_destroy.restype = None
     L.tvl1_set_params.argtypes = [_vp, C.POINTER(Params)]
     L.tvl1_set_timing.argtypes = [_vp, C.c_int]
+    L.tvl1_set_option.argtypes = [_vp, C.c_char_p, C.c_double]
     L.tvl1_calc_u8.argtypes = [_vp, _vp, _sz, _vp, _sz, C.c_int, C.c_int, _vp, _vp, _sz, _vp,
                                C.POINTER(Stats)]
     L.tvl1_calc_u8_host.argtypes = [_vp, _vp, _sz, _vp, _sz, C.c_int, C.c_int, _vp, _vp, _sz,
@@ -119,6 +127,7 @@ def lib():
     L.tvl1_k_warp.argtypes = [_vp] * 4 + [C.c_int, C.c_int, C.c_int] + [_vp] * 6
     L.tvl1_k_iterate.argtypes = [_vp] * 10 + [C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
                                               C.c_float, C.c_int, _vp, _vp]
+    L.tvl1_k_iterate_fused2.argtypes = L.tvl1_k_iterate.argtypes
     L.tvl1_k_median5.argtypes = [_vp, C.c_int, C.c_int, C.c_int, _vp, _vp]
     L.tvl1_k_last_ms.argtypes = [C.POINTER(C.c_float)]
     L.tvl1_pyramid_sizes.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, _vp, _vp]
@@ -280,6 +289,9 @@ class Solver:
         except Exception:
             pass
 
+    def set_option(self, key, value):
+        check(lib().tvl1_set_option(self.handle, key.encode(), float(value)))
+
     def set_params(self, params):
         check(lib().tvl1_set_params(self.handle, C.byref(params)))
         self.params = params
@@ -433,14 +445,16 @@ def k_warp(I0, I1, u1, u2, device=0):
     return tuple(p.get() for p in outs)
 
 
-def k_iterate(I1wx, I1wy, grad, rho_c, u1, u2, p11, p12, p21, p22, l_t, theta, taut, n=1, device=0):
-    """n iterations; returns (u1,u2,p11,p12,p21,p22, errors[n])."""
+def k_iterate(I1wx, I1wy, grad, rho_c, u1, u2, p11, p12, p21, p22, l_t, theta, taut, n=1, device=0,
+              fused=False):
+    """n iterations; returns (u1,u2,p11,p12,p21,p22, errors[n]).  fused: two per launch."""
     h, w = np.asarray(u1).shape
     consts = [Plane(h, w, device, np.asarray(a, np.float32)) for a in (I1wx, I1wy, grad, rho_c)]
     state = [Plane(h, w, device, np.asarray(a, np.float32)) for a in (u1, u2, p11, p12, p21, p22)]
     errs = np.zeros(max(n, 1), np.float64)
-    check(lib().tvl1_k_iterate(*[p.ptr for p in consts], *[p.ptr for p in state], w, h,
-                               state[0].pitch, l_t, theta, taut, n, errs.ctypes.data, None))
+    fn = lib().tvl1_k_iterate_fused2 if fused else lib().tvl1_k_iterate
+    check(fn(*[p.ptr for p in consts], *[p.ptr for p in state], w, h,
+             state[0].pitch, l_t, theta, taut, n, errs.ctypes.data, None))
     return tuple(p.get() for p in state) + (errs[:n],)
 
 

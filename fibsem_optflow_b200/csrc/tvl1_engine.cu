@@ -175,6 +175,48 @@ int launch_iterate(IterArgs& a, cudaStream_t st)
     return TVL1_OK;
 }
 
+static int iterate2_resident_blocks()
+{
+    static int cached = 0;
+    if (cached) return cached;
+    int dev = 0, sms = 148, occ = 3;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_iterate2<ITER_NW>, 32 * ITER_NW, 0) != cudaSuccess || occ < 1)
+        occ = 3;
+    cached = sms * occ;
+    return cached;
+}
+
+// the fused kernel pays 3 halo rows per tile: tall tiles, as evenly spread as possible
+static int iterate2_rows(int w, int h, int resident, int* grid)
+{
+    static const int cand[] = {8, 12, 16, 20, 24, 28, 32, 40, 48, 64};
+    const int gx = cdiv(cdiv(w, TVL1_STRIP2), ITER_NW);
+    double best = -1.0;
+    int best_r = 16, best_g = 1;
+    for (int R : cand) {
+        const long long ntiles = (long long)gx * cdiv(h, R);
+        const long long G = ntiles < resident ? ntiles : resident;
+        const long long rounds = (ntiles + G - 1) / G;
+        double eff = (double)ntiles / (double)(rounds * G) * (double)R / (double)(R + 3);
+        if (G < resident) eff *= (double)G / resident;
+        if (eff >= best) { best = eff; best_r = R; best_g = (int)G; }
+    }
+    *grid = best_g;
+    return best_r;
+}
+
+int launch_iterate2(IterArgs& a, cudaStream_t st)
+{
+    int grid = 1;
+    a.rows = iterate2_rows(a.w, a.h, iterate2_resident_blocks(), &grid);
+    dim3 b(32, ITER_NW);
+    k_iterate2<ITER_NW><<<grid, b, 0, st>>>(a);
+    CK(cudaGetLastError());
+    return TVL1_OK;
+}
+
 int launch_median(const MedianArgs& a, int planes, cudaStream_t st)
 {
     dim3 b(32, 8);
@@ -200,6 +242,7 @@ struct tvl1_handle {
     tvl1_params prm;
     int inner = 30, outer = 10;
     bool timing = false;
+    long long fused_min_px = 4000000;   // levels at least this large use the two-iteration kernel
     // arena
     char* arena = nullptr;
     size_t arena_bytes = 0;
@@ -410,6 +453,8 @@ static int calc_device(tvl1_handle* H, const uint8_t* f0, size_t pitch0, const u
         ia.w = lv.w; ia.h = lv.h; ia.pitch = lv.pitch;
         ia.l_t = l_t; ia.theta = theta; ia.taut = taut; ia.scaled_eps = scaled_eps;
         ia.level = s; ia.ctrl = H->d_ctrl; ia.partials = H->d_partials; ia.errlog = nullptr;
+        ia.mode = 0; ia.inner_max = H->inner;
+        const bool fused = (long long)lv.w * lv.h >= H->fused_min_px && H->inner >= 2;
         MedianArgs ma;
         ma.u1[0] = lv.u1; ma.u1[1] = H->u1x; ma.u2[0] = lv.u2; ma.u2[1] = H->u2x;
         ma.w = lv.w; ma.h = lv.h; ma.pitch = lv.pitch; ma.level = s; ma.ctrl = H->d_ctrl;
@@ -439,13 +484,41 @@ static int calc_device(tvl1_handle* H, const uint8_t* f0, size_t pitch0, const u
                     span_end();
                 }
                 if ((rc = span_begin(0, s))) return rc;
-                for (int ni = 0; ni < H->inner; ++ni) {
-                    if ((rc = launch_iterate(ia, st))) return rc;
+                // a new outer iteration: no inner iteration done yet (the fused schedule counts them)
+                CK(cudaMemsetAsync(&H->d_ctrl->inner, 0, sizeof(int), st));
+                if (fused) {
+                    // temporally blocked schedule: [fused pair | single] slots, then a tail of
+                    // singles that covers the all-single worst case.  Which slots really run is
+                    // decided on the device (stop imminent / overshoot replay / iterations left).
+                    IterArgs i2 = ia, i1 = ia, i3 = ia;
+                    i2.mode = 2; i1.mode = 1; i3.mode = 3;
+                    const int groups = H->inner / 2;
+                    for (int k = 0; k < groups; ++k) {
+                        if ((rc = launch_iterate2(i2, st))) return rc;
+                        if ((rc = launch_iterate(i1, st))) return rc;
+                    }
+                    for (int k = 0; k < H->inner - groups; ++k)
+                        if ((rc = launch_iterate(i3, st))) return rc;
+                    launches += 2 * groups + (H->inner - groups);
+                } else {
+                    for (int ni = 0; ni < H->inner; ++ni) {
+                        if ((rc = launch_iterate(ia, st))) return rc;
+                    }
+                    launches += H->inner;
                 }
-                launches += H->inner;
                 span_end();
                 CK(cudaMemcpyAsync(H->h_ctrl, H->d_ctrl, hdr, cudaMemcpyDeviceToHost, st));
                 CK(cudaStreamSynchronize(st));
+                while (fused && !H->h_ctrl->done && H->h_ctrl->inner < H->inner) {
+                    // cannot happen with the slot counts above; kept so that a median is never
+                    // applied before the outer iteration is complete
+                    IterArgs i3 = ia;
+                    i3.mode = 3;
+                    if ((rc = launch_iterate(i3, st))) return rc;
+                    launches++;
+                    CK(cudaMemcpyAsync(H->h_ctrl, H->d_ctrl, hdr, cudaMemcpyDeviceToHost, st));
+                    CK(cudaStreamSynchronize(st));
+                }
                 if (H->h_ctrl->done) break;
             }
         }
@@ -591,6 +664,13 @@ int tvl1_set_params(tvl1_handle* H, const tvl1_params* p)
     if (rc) return rc;
     H->prm = *p;
     return resolve_iterations(H);
+}
+
+int tvl1_set_option(tvl1_handle* H, const char* key, double value)
+{
+    if (!H || !key) return fail(TVL1_ERR_INVALID, "null handle or key");
+    if (!strcmp(key, "fused_min_px")) { H->fused_min_px = value < 0 ? 0 : (long long)value; return TVL1_OK; }
+    return fail(TVL1_ERR_INVALID, "unknown option '%s'", key);
 }
 
 int tvl1_set_timing(tvl1_handle* H, int enabled)
@@ -815,7 +895,7 @@ int tvl1_k_warp(const float* d_I0, const float* d_I1, const float* d_u1, const f
     return rc;
 }
 
-int tvl1_k_iterate(const float* d_I1wx, const float* d_I1wy, const float* d_grad, const float* d_rho_c,
+static int k_iterate_impl(int fused, const float* d_I1wx, const float* d_I1wy, const float* d_grad, const float* d_rho_c,
                    float* d_u1, float* d_u2, float* d_p11, float* d_p12, float* d_p21, float* d_p22,
                    int w, int h, int pitch, float l_t, float theta, float taut, int n, double* errors, void* stream)
 {
@@ -842,15 +922,16 @@ int tvl1_k_iterate(const float* d_I1wx, const float* d_I1wy, const float* d_grad
     a.p21[0] = d_p21; a.p21[1] = tw[4]; a.p22[0] = d_p22; a.p22[1] = tw[5];
     a.w = w; a.h = h; a.pitch = pitch; a.l_t = l_t; a.theta = theta; a.taut = taut;
     a.scaled_eps = -1.f;   // never stops
-    a.level = 0; a.slot = 0;
+    a.level = 0; a.slot = 0; a.mode = 0; a.inner_max = 1 << 30;
     a.ctrl = (Ctrl*)(tmp + ctrl_off);
     a.partials = (double*)(tmp + part_off);
     a.errlog = (double*)(tmp + log_off);
     int rc = TVL1_OK;
     stage_begin(st);
-    for (int i = 0; i < n && !rc; i++) rc = launch_iterate(a, st);
+    if (fused) { for (int i = 0; i + 1 < n && !rc; i += 2) rc = launch_iterate2(a, st); }
+    else { for (int i = 0; i < n && !rc; i++) rc = launch_iterate(a, st); }
     stage_end(st);
-    if (!rc && (n & 1)) {
+    if (!rc && ((fused ? n / 2 : n) & 1)) {
         float* dst[6] = {d_u1, d_u2, d_p11, d_p12, d_p21, d_p22};
         for (int k = 0; k < 6 && !rc; k++)
             if (cudaMemcpyAsync(dst[k], tw[k], pb, cudaMemcpyDeviceToDevice, st) != cudaSuccess)
@@ -863,6 +944,24 @@ int tvl1_k_iterate(const float* d_I1wx, const float* d_I1wy, const float* d_grad
     if (!rc && e != cudaSuccess) rc = fail(TVL1_ERR_CUDA, "iterate: %s", cudaGetErrorString(e));
     cudaFree(tmp);
     return rc;
+}
+
+int tvl1_k_iterate(const float* d_I1wx, const float* d_I1wy, const float* d_grad, const float* d_rho_c,
+                   float* d_u1, float* d_u2, float* d_p11, float* d_p12, float* d_p21, float* d_p22,
+                   int w, int h, int pitch, float l_t, float theta, float taut, int n, double* errors, void* stream)
+{
+    return k_iterate_impl(0, d_I1wx, d_I1wy, d_grad, d_rho_c, d_u1, d_u2, d_p11, d_p12, d_p21, d_p22, w, h, pitch,
+                          l_t, theta, taut, n, errors, stream);
+}
+
+int tvl1_k_iterate_fused2(const float* d_I1wx, const float* d_I1wy, const float* d_grad, const float* d_rho_c,
+                          float* d_u1, float* d_u2, float* d_p11, float* d_p12, float* d_p21, float* d_p22,
+                          int w, int h, int pitch, float l_t, float theta, float taut, int n, double* errors,
+                          void* stream)
+{
+    if (n & 1) return fail(TVL1_ERR_INVALID, "the fused kernel advances two iterations per launch: n must be even");
+    return k_iterate_impl(1, d_I1wx, d_I1wy, d_grad, d_rho_c, d_u1, d_u2, d_p11, d_p12, d_p21, d_p22, w, h, pitch,
+                          l_t, theta, taut, n, errors, stream);
 }
 
 int tvl1_k_median5(const float* d_src, int w, int h, int pitch, float* d_dst, void* stream)

@@ -92,6 +92,10 @@ void tvl1_default_params(tvl1_params* p);
 int tvl1_create(const tvl1_params* p, int device, tvl1_handle** out);
 void tvl1_destroy(tvl1_handle* h);
 int tvl1_set_params(tvl1_handle* h, const tvl1_params* p);
+/* Tuning knobs that never change results.  "fused_min_px": pyramid levels with at least this
+ * many pixels run the temporally blocked two-iteration kernel (default 4e6; 0 = always,
+ * 1e18 = never). */
+int tvl1_set_option(tvl1_handle* h, const char* key, double value);
 /* per-stage CUDA-event timing in tvl1_stats (adds stream syncs); default off */
 int tvl1_set_timing(tvl1_handle* h, int enabled);
 
@@ -185,6 +189,11 @@ int tvl1_k_iterate(const float* d_I1wx, const float* d_I1wy, const float* d_grad
                    const float* d_rho_c, float* d_u1, float* d_u2, float* d_p11, float* d_p12,
                    float* d_p21, float* d_p22, int w, int h, int pitch,
                    float l_t, float theta, float taut, int n, double* errors, void* stream);
+/* same through the temporally blocked kernel (two iterations per launch); n must be even */
+int tvl1_k_iterate_fused2(const float* d_I1wx, const float* d_I1wy, const float* d_grad,
+                          const float* d_rho_c, float* d_u1, float* d_u2, float* d_p11, float* d_p12,
+                          float* d_p21, float* d_p22, int w, int h, int pitch,
+                          float l_t, float theta, float taut, int n, double* errors, void* stream);
 int tvl1_k_median5(const float* d_src, int w, int h, int pitch, float* d_dst, void* stream);
 /* CUDA-event time of the kernel launches of the calling thread's most recent tvl1_k_warp /
  * tvl1_k_iterate / tvl1_k_median5 call (waits for them). */

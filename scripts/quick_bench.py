@@ -7,6 +7,8 @@ from fibsem_optflow_b200 import _native as N, synth
 def run(h, w, nscales, reps=2):
     t = time.time(); I0, I1 = synth.make_pair(h, w, seed=7, shear=4.0/h); tg = time.time() - t
     s = N.Solver(N.default_params(lambda_=0.15, nscales=nscales, inner_iterations=30, outer_iterations=10))
+    if os.environ.get("FUSED_MIN_PX"):
+        s.set_option("fused_min_px", float(os.environ["FUSED_MIN_PX"]))
     for r in range(reps):
         t = time.time(); u, v = s.calc(I0, I1); dt = time.time() - t
         st = s.stats

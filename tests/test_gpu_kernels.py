@@ -91,3 +91,19 @@ def test_iterate(gpu, orc, h, w, n):
     for k in range(6):
         assert np.array_equal(got[k], want[k]), names[k]
     np.testing.assert_allclose(got[6], werr, rtol=1e-12)
+
+
+@pytest.mark.parametrize("h,w", SIZES + [(200, 700)])
+@pytest.mark.parametrize("n", [2, 6])
+def test_iterate_fused2(gpu, orc, h, w, n):
+    """temporally blocked kernel (two iterations per launch): same states, same per-iteration errors"""
+    rng = np.random.default_rng(5)
+    consts, state = make_iter_inputs(rng, h, w)
+    l_t, theta, taut = np.float32(0.15 * 0.3), np.float32(0.3), np.float32(0.25 / 0.3)
+    want = [s.copy() for s in state]
+    werr = [orc.iterate(*consts, *want, l_t, theta, taut) for _ in range(n)]
+    got = gpu.k_iterate(*consts, *state, l_t, theta, taut, n=n, fused=True)
+    names = ["u1", "u2", "p11", "p12", "p21", "p22"]
+    for k in range(6):
+        assert np.array_equal(got[k], want[k]), names[k]
+    np.testing.assert_allclose(got[6], werr, rtol=1e-12)

@@ -74,3 +74,28 @@ def test_errors(gpu):
     s = gpu.Solver(gpu.default_params())
     with pytest.raises(gpu.Tvl1Error):
         s.calc(np.zeros((8, 8), np.uint8), np.zeros((8, 9), np.uint8))
+
+
+@pytest.mark.parametrize("h,w,seed,kw", [
+    (256, 320, 7, dict(lambda_=0.15, nscales=5)),
+    (300, 200, 3, dict(lambda_=0.15, nscales=4, inner_iterations=7, outer_iterations=12)),   # odd inner
+    (200, 260, 9, dict()),                                                                   # wrapper defaults
+    (128, 160, 2, dict(lambda_=0.15, nscales=3, median_filtering=1, inner_iterations=40, outer_iterations=2)),
+    (96, 130, 4, dict(lambda_=0.15, nscales=2, epsilon=0.05)),                               # stops within 1-3 iterations
+])
+def test_fused_schedule_is_exact(gpu, orc, h, w, seed, kw):
+    """The temporally blocked schedule (two iterations per launch, device-side replay when the first
+    of the two already meets the stop test) must reproduce the per-iteration stop exactly."""
+    I0, I1 = synth.make_pair(h, w, seed=seed)
+    s = gpu.Solver(gpu.default_params(**kw))
+    s.set_option("fused_min_px", 0)                      # force it on every level
+    u, v = s.calc(I0, I1)
+    okw = {("lambda" if k == "lambda_" else k): val for k, val in kw.items()}
+    if "lambda" not in okw:
+        okw.update({"lambda": 0.05, "nscales": 10})
+    ou, ov, oit, olev = orc.tvl1_calc(I0, I1, **okw)
+    assert s.stats.levels == olev
+    assert np.array_equal(s.stats.iters_array(), oit[:olev])
+    assert np.array_equal(u, ou) and np.array_equal(v, ov)
+    with pytest.raises(gpu.Tvl1Error):
+        s.set_option("no_such_option", 1)
