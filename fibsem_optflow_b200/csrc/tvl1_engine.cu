@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -129,90 +130,75 @@ int launch_warp(const WarpArgs& a, cudaStream_t st)
 #endif
 static const int ITER_NW = TVL1_ITER_NW;
 
-// resident blocks of k_iterate on this device (SMs x occupancy), queried once
-static int iterate_resident_blocks()
+// resident blocks of the iteration kernels on the current device (SMs x occupancy), queried once
+// per device; the fused kernel's shared-memory ring needs the opt-in limit raised first
+static int resident_blocks(bool fused)
 {
-    static int cached = 0;
-    if (cached) return cached;
-    int dev = 0, sms = 148, occ = 4;
+    static int cached[2][64] = {};
+    int dev = 0, sms = 148, occ = 0;
     cudaGetDevice(&dev);
+    int& c = cached[fused ? 1 : 0][dev & 63];
+    if (c) return c;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_iterate<ITER_NW>, 32 * ITER_NW, 0) != cudaSuccess || occ < 1)
-        occ = 4;
-    cached = sms * occ;
-    return cached;
+    cudaError_t e;
+    if (fused) {
+        cudaFuncSetAttribute(k_iterate2<ITER_NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, TVL1_RING_BYTES(ITER_NW));
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_iterate2<ITER_NW>, 32 * ITER_NW, TVL1_RING_BYTES(ITER_NW));
+    } else {
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_iterate<ITER_NW>, 32 * ITER_NW, 0);
+    }
+    if (e != cudaSuccess || occ < 1) occ = fused ? 3 : 4;
+    c = sms * occ;
+    return c;
 }
 
 size_t iterate_max_blocks(int, int) { return 148 * 32 * 2; }
 
-// rows per tile: tall tiles amortise the bottom-halo row (R/(R+1)), but the tile count has to
-// divide evenly over the resident blocks (grid-stride loop, no partial last round)
-static int iterate_rows(int w, int h, int resident, int* grid)
+// Rows per tile and grid size.  A tile is one warp's strip x R rows and every resident warp walks
+// the tile list with a grid stride: tall tiles amortise the halo rows (R / (R + halo)), but the
+// tile count has to spread evenly over the resident warps (no nearly empty last round).
+static int tile_rows(int w, int h, int strip, int halo, int rmin, int resident_blocks, int* grid)
 {
-    static const int cand[] = {4, 5, 6, 7, 8, 10, 12, 14, 16, 20, 24, 28, 32};
-    const int gx = cdiv(cdiv(w, TVL1_STRIP), ITER_NW);
+    const long long ns = cdiv(w, strip);
+    const long long slots = (long long)resident_blocks * ITER_NW;
     double best = -1.0;
-    int best_r = 4, best_g = 1;
-    for (int R : cand) {
-        const long long ntiles = (long long)gx * cdiv(h, R);
-        const long long G = ntiles < resident ? ntiles : resident;
+    int best_r = rmin;
+    long long best_g = 1;
+    for (int R = rmin; R <= 64; ++R) {
+        const long long ntiles = ns * cdiv(h, R);
+        const long long G = ntiles < slots ? ntiles : slots;   // warps that get work
         const long long rounds = (ntiles + G - 1) / G;
-        double eff = (double)ntiles / (double)(rounds * G) * (double)R / (double)(R + 1);
-        if (G < resident) eff *= (double)G / resident;   // not even one block per slot
-        if (eff >= best) { best = eff; best_r = R; best_g = (int)G; }
+        double eff = (double)ntiles / (double)(rounds * G) * (double)R / (double)(R + halo);
+        if (G < slots) eff *= (double)G / (double)slots;       // not even one tile per warp
+        if (eff >= best) { best = eff; best_r = R; best_g = G; }
     }
-    *grid = best_g;
+    if (const char* e = getenv(halo == 1 ? "TVL1_DEV_ROWS" : "TVL1_DEV_ROWS2")) {   // developer sweeps only
+        best_r = atoi(e);
+        const long long ntiles = ns * cdiv(h, best_r);
+        best_g = ntiles < slots ? ntiles : slots;
+    }
+    if (getenv("TVL1_DEV_VERBOSE"))
+        fprintf(stderr, "tile_rows %dx%d strip %d: R=%d warps=%lld tiles=%lld\n", w, h, strip, best_r, best_g, ns * cdiv(h, best_r));
+    *grid = (int)((best_g + ITER_NW - 1) / ITER_NW);
     return best_r;
 }
 
 int launch_iterate(IterArgs& a, cudaStream_t st)
 {
     int grid = 1;
-    a.rows = iterate_rows(a.w, a.h, iterate_resident_blocks(), &grid);
+    a.rows = tile_rows(a.w, a.h, TVL1_STRIP, 1, 4, resident_blocks(false), &grid);
     dim3 b(32, ITER_NW);
     k_iterate<ITER_NW><<<grid, b, 0, st>>>(a);
     CK(cudaGetLastError());
     return TVL1_OK;
 }
 
-static int iterate2_resident_blocks()
-{
-    static int cached = 0;
-    if (cached) return cached;
-    int dev = 0, sms = 148, occ = 3;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_iterate2<ITER_NW>, 32 * ITER_NW, 0) != cudaSuccess || occ < 1)
-        occ = 3;
-    cached = sms * occ;
-    return cached;
-}
-
-// the fused kernel pays 3 halo rows per tile: tall tiles, as evenly spread as possible
-static int iterate2_rows(int w, int h, int resident, int* grid)
-{
-    static const int cand[] = {8, 12, 16, 20, 24, 28, 32, 40, 48, 64};
-    const int gx = cdiv(cdiv(w, TVL1_STRIP2), ITER_NW);
-    double best = -1.0;
-    int best_r = 16, best_g = 1;
-    for (int R : cand) {
-        const long long ntiles = (long long)gx * cdiv(h, R);
-        const long long G = ntiles < resident ? ntiles : resident;
-        const long long rounds = (ntiles + G - 1) / G;
-        double eff = (double)ntiles / (double)(rounds * G) * (double)R / (double)(R + 3);
-        if (G < resident) eff *= (double)G / resident;
-        if (eff >= best) { best = eff; best_r = R; best_g = (int)G; }
-    }
-    *grid = best_g;
-    return best_r;
-}
-
 int launch_iterate2(IterArgs& a, cudaStream_t st)
 {
     int grid = 1;
-    a.rows = iterate2_rows(a.w, a.h, iterate2_resident_blocks(), &grid);
+    a.rows = tile_rows(a.w, a.h, TVL1_STRIP2, 3, 8, resident_blocks(true), &grid);   // 3 halo rows per tile
     dim3 b(32, ITER_NW);
-    k_iterate2<ITER_NW><<<grid, b, 0, st>>>(a);
+    k_iterate2<ITER_NW><<<grid, b, TVL1_RING_BYTES(ITER_NW), st>>>(a);
     CK(cudaGetLastError());
     return TVL1_OK;
 }
