@@ -132,22 +132,28 @@ static const int ITER_NW = TVL1_ITER_NW;
 
 // resident blocks of the iteration kernels on the current device (SMs x occupancy), queried once
 // per device; the fused kernel's shared-memory ring needs the opt-in limit raised first
-static int resident_blocks(bool fused)
+enum { KI_SMALL = 0, KI_LARGE = 1, KI_FUSED = 2 };   // k_iterate<.,5>, k_iterate<.,4>, k_iterate2
+static const long long ITER_LARGE_PX = 16000000;     // levels at least this large: 4 blocks per SM
+
+static int resident_blocks(int which)
 {
-    static int cached[2][64] = {};
+    static int cached[3][64] = {};
     int dev = 0, sms = 148, occ = 0;
     cudaGetDevice(&dev);
-    int& c = cached[fused ? 1 : 0][dev & 63];
+    int& c = cached[which][dev & 63];
     if (c) return c;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaError_t e;
-    if (fused) {
+    if (which == KI_FUSED) {
+        // the shared-memory ring needs the opt-in limit raised first
         cudaFuncSetAttribute(k_iterate2<ITER_NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, TVL1_RING_BYTES(ITER_NW));
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_iterate2<ITER_NW>, 32 * ITER_NW, TVL1_RING_BYTES(ITER_NW));
+    } else if (which == KI_LARGE) {
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_iterate<ITER_NW, 4>, 32 * ITER_NW, 0);
     } else {
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_iterate<ITER_NW>, 32 * ITER_NW, 0);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_iterate<ITER_NW, 5>, 32 * ITER_NW, 0);
     }
-    if (e != cudaSuccess || occ < 1) occ = fused ? 3 : 4;
+    if (e != cudaSuccess || occ < 1) occ = which == KI_FUSED ? 3 : 4;
     c = sms * occ;
     return c;
 }
@@ -186,9 +192,11 @@ static int tile_rows(int w, int h, int strip, int halo, int rmin, int resident_b
 int launch_iterate(IterArgs& a, cudaStream_t st)
 {
     int grid = 1;
-    a.rows = tile_rows(a.w, a.h, TVL1_STRIP, 1, 4, resident_blocks(false), &grid);
+    const bool large = (long long)a.w * a.h >= ITER_LARGE_PX;
+    a.rows = tile_rows(a.w, a.h, TVL1_STRIP, 1, 4, resident_blocks(large ? KI_LARGE : KI_SMALL), &grid);
     dim3 b(32, ITER_NW);
-    k_iterate<ITER_NW><<<grid, b, 0, st>>>(a);
+    if (large) k_iterate<ITER_NW, 4><<<grid, b, 0, st>>>(a);
+    else k_iterate<ITER_NW, 5><<<grid, b, 0, st>>>(a);
     CK(cudaGetLastError());
     return TVL1_OK;
 }
@@ -196,7 +204,7 @@ int launch_iterate(IterArgs& a, cudaStream_t st)
 int launch_iterate2(IterArgs& a, cudaStream_t st)
 {
     int grid = 1;
-    a.rows = tile_rows(a.w, a.h, TVL1_STRIP2, 3, 8, resident_blocks(true), &grid);   // 3 halo rows per tile
+    a.rows = tile_rows(a.w, a.h, TVL1_STRIP2, 3, 8, resident_blocks(KI_FUSED), &grid);   // 3 halo rows per tile
     dim3 b(32, ITER_NW);
     k_iterate2<ITER_NW><<<grid, b, TVL1_RING_BYTES(ITER_NW), st>>>(a);
     CK(cudaGetLastError());
@@ -228,7 +236,7 @@ struct tvl1_handle {
     tvl1_params prm;
     int inner = 30, outer = 10;
     bool timing = false;
-    long long fused_min_px = 4000000;   // levels at least this large use the two-iteration kernel
+    long long fused_min_px = 1500000;   // levels at least this large use the two-iteration kernel (measured cross-over ~1.2 Mpx)
     // arena
     char* arena = nullptr;
     size_t arena_bytes = 0;
@@ -424,6 +432,7 @@ static int calc_device(tvl1_handle* H, const uint8_t* f0, size_t pitch0, const u
     CK(cudaEventRecord(ev_pyr, st));
 
     const size_t hdr = offsetof(Ctrl, iters);
+    std::vector<int> counts((size_t)L * W, 0);   // iterations each (level, warp) needed
     for (int s = L - 1; s >= 0; --s) {
         const Level& lv = H->lv[s];
         const size_t pb = (size_t)lv.pitch * lv.h * sizeof(float);
@@ -459,9 +468,14 @@ static int calc_device(tvl1_handle* H, const uint8_t* f0, size_t pitch0, const u
             if ((rc = launch_warp(wa, st))) return rc;
             launches++;
             span_end();
-            // (3) outer iterations: median + `inner` primal-dual iterations, each kernel a
-            // no-op once the device-side stop flag is set; one host read-back per outer
-            // iteration decides whether another is needed.
+            // (3) outer iterations: median + up to `inner` primal-dual iterations.  Every kernel is a
+            // no-op once the device-side stop flag is set, so iterations are enqueued in chunks without
+            // knowing how many will really run; the first chunk is sized by the count the previous
+            // warp (or, for the first warp, the coarser level) needed, and one 32-byte read-back per
+            // chunk tells the host whether more are wanted.  The stop iteration is exactly the
+            // oracle's; a wrong guess costs a few no-op launches or one extra host round trip.
+            const int pred_total = wi > 0 ? counts[slot - 1] : (s < L - 1 ? counts[(s + 1) * W] : H->inner);
+            int done_total = 0;
             for (int no = 0; no < H->outer; ++no) {
                 if (P.median_filtering > 1) {
                     if ((rc = span_begin(2, s))) return rc;
@@ -470,43 +484,43 @@ static int calc_device(tvl1_handle* H, const uint8_t* f0, size_t pitch0, const u
                     span_end();
                 }
                 if ((rc = span_begin(0, s))) return rc;
-                // a new outer iteration: no inner iteration done yet (the fused schedule counts them)
+                // a new outer iteration: no inner iteration done yet
                 CK(cudaMemsetAsync(&H->d_ctrl->inner, 0, sizeof(int), st));
-                if (fused) {
-                    // temporally blocked schedule: [fused pair | single] slots, then a tail of
-                    // singles that covers the all-single worst case.  Which slots really run is
-                    // decided on the device (stop imminent / overshoot replay / iterations left).
-                    IterArgs i2 = ia, i1 = ia, i3 = ia;
-                    i2.mode = 2; i1.mode = 1; i3.mode = 3;
-                    const int groups = H->inner / 2;
-                    for (int k = 0; k < groups; ++k) {
-                        if ((rc = launch_iterate2(i2, st))) return rc;
-                        if ((rc = launch_iterate(i1, st))) return rc;
+                int done_inner = 0, want = 0;
+                for (;;) {
+                    const int left_pred = pred_total - done_total - done_inner;
+                    want = want == 0 ? (left_pred + 1 > 4 ? left_pred + 1 : 4) : 2 * want;
+                    if (want > H->inner - done_inner) want = H->inner - done_inner;
+                    if (fused) {
+                        // temporally blocked schedule: [fused pair | single] slot pairs.  Which slot
+                        // of a pair really runs is decided on the device: the pair while the stop is
+                        // not imminent and two iterations still fit, the single after an overshoot
+                        // (replay), near the stop, or for the last iteration.
+                        IterArgs i2 = ia, i1 = ia;
+                        i2.mode = 2; i1.mode = 1;
+                        const int groups = (want + 1) / 2;
+                        for (int k = 0; k < groups; ++k) {
+                            if ((rc = launch_iterate2(i2, st))) return rc;
+                            if ((rc = launch_iterate(i1, st))) return rc;
+                        }
+                        launches += 2 * groups;
+                    } else {
+                        IterArgs i3 = ia;
+                        i3.mode = 3;
+                        for (int k = 0; k < want; ++k)
+                            if ((rc = launch_iterate(i3, st))) return rc;
+                        launches += want;
                     }
-                    for (int k = 0; k < H->inner - groups; ++k)
-                        if ((rc = launch_iterate(i3, st))) return rc;
-                    launches += 2 * groups + (H->inner - groups);
-                } else {
-                    for (int ni = 0; ni < H->inner; ++ni) {
-                        if ((rc = launch_iterate(ia, st))) return rc;
-                    }
-                    launches += H->inner;
-                }
-                span_end();
-                CK(cudaMemcpyAsync(H->h_ctrl, H->d_ctrl, hdr, cudaMemcpyDeviceToHost, st));
-                CK(cudaStreamSynchronize(st));
-                while (fused && !H->h_ctrl->done && H->h_ctrl->inner < H->inner) {
-                    // cannot happen with the slot counts above; kept so that a median is never
-                    // applied before the outer iteration is complete
-                    IterArgs i3 = ia;
-                    i3.mode = 3;
-                    if ((rc = launch_iterate(i3, st))) return rc;
-                    launches++;
                     CK(cudaMemcpyAsync(H->h_ctrl, H->d_ctrl, hdr, cudaMemcpyDeviceToHost, st));
                     CK(cudaStreamSynchronize(st));
+                    done_inner = H->h_ctrl->inner;
+                    if (H->h_ctrl->done || done_inner >= H->inner) break;
                 }
+                span_end();
+                done_total += done_inner;
                 if (H->h_ctrl->done) break;
             }
+            counts[slot] = done_total;
         }
         if (s == 0) break;
         // flow upsample to the next finer level (A.2): resize to its size, times 1/scaleStep

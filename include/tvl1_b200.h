@@ -93,7 +93,7 @@ int tvl1_create(const tvl1_params* p, int device, tvl1_handle** out);
 void tvl1_destroy(tvl1_handle* h);
 int tvl1_set_params(tvl1_handle* h, const tvl1_params* p);
 /* Tuning knobs that never change results.  "fused_min_px": pyramid levels with at least this
- * many pixels run the temporally blocked two-iteration kernel (default 4e6; 0 = always,
+ * many pixels run the temporally blocked two-iteration kernel (default 1.5e6; 0 = always,
  * 1e18 = never). */
 int tvl1_set_option(tvl1_handle* h, const char* key, double value);
 /* per-stage CUDA-event timing in tvl1_stats (adds stream syncs); default off */
