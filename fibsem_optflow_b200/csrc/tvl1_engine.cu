@@ -433,6 +433,8 @@ static int calc_device(tvl1_handle* H, const uint8_t* f0, size_t pitch0, const u
 
     const size_t hdr = offsetof(Ctrl, iters);
     std::vector<int> counts((size_t)L * W, 0);   // iterations each (level, warp) needed
+    double* dev_errlog = nullptr;                // developer aid: per-iteration error sums to stderr
+    if (getenv("TVL1_DEV_ERRLOG")) cudaMalloc(&dev_errlog, sizeof(double) * L * W * H->inner * H->outer);
     for (int s = L - 1; s >= 0; --s) {
         const Level& lv = H->lv[s];
         const size_t pb = (size_t)lv.pitch * lv.h * sizeof(float);
@@ -462,6 +464,7 @@ static int calc_device(tvl1_handle* H, const uint8_t* f0, size_t pitch0, const u
         for (int wi = 0; wi < W; ++wi) {
             const int slot = s * W + wi;
             ia.slot = slot;
+            if (dev_errlog) ia.errlog = dev_errlog + (size_t)slot * H->inner * H->outer;
             ma.slot = slot;
             // (2) warp I1 by the current flow; also re-arms the stop test (error = FLT_MAX)
             if ((rc = span_begin(1, s))) return rc;
@@ -521,8 +524,15 @@ static int calc_device(tvl1_handle* H, const uint8_t* f0, size_t pitch0, const u
                 if (H->h_ctrl->done) break;
             }
             counts[slot] = done_total;
+            if (dev_errlog && done_total > 0) {
+                std::vector<double> e(done_total);
+                cudaMemcpy(e.data(), ia.errlog, sizeof(double) * done_total, cudaMemcpyDeviceToHost);
+                fprintf(stderr, "errlog L%d w%d n=%d e/eps:", s, wi, done_total);
+                for (int k = 0; k < done_total; k++) fprintf(stderr, " %.3g", e[k] / scaled_eps);
+                fprintf(stderr, "\n");
+            }
         }
-        if (s == 0) break;
+        if (s == 0) { if (dev_errlog) cudaFree(dev_errlog); break; }
         // flow upsample to the next finer level (A.2): resize to its size, times 1/scaleStep
         const Level& up = H->lv[s - 1];
         const int uc = H->h_ctrl->ucur[s];

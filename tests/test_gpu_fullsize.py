@@ -1,0 +1,89 @@
+"""Parity at BASELINE.json's sizes.
+
+* configs[0] (2048^2, DualTVL1 defaults) is small enough for the C oracle (a few seconds on the
+  box's host cores): bit-exact flow and iteration counts.
+* configs[1] (8192^2, 6 scales) would keep the oracle busy for a minute, so it is checked through
+  properties that do not depend on the size: the temporally blocked schedule and the plain
+  one-iteration-per-launch schedule must agree bit for bit (flow and every iteration count), a
+  second run on the same handle must reproduce the first, the flow must recover the analytic
+  displacement of the synthetic pair, and away from the border of a centre crop it must agree
+  with the oracle's solve of that crop.
+* a config[3]-style pair (8 scales, 10 warps, 8-20 px displacement) at a size the oracle finishes:
+  exercises the warp kernel's wide-window fallback.
+"""
+import numpy as np
+import pytest
+
+from fibsem_optflow_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def test_config0_2048_exact(gpu, orc):
+    I0, I1 = synth.make_pair(2048, 2048, seed=7)
+    s = gpu.Solver(gpu.default_params(lambda_=0.15, nscales=5, inner_iterations=30, outer_iterations=10))
+    u, v = s.calc(I0, I1)
+    ou, ov, oit, olev = orc.tvl1_calc(I0, I1, **{"lambda": 0.15, "nscales": 5})
+    assert s.stats.levels == olev == 5
+    assert np.array_equal(s.stats.iters_array(), oit[:olev])
+    assert np.array_equal(u, ou) and np.array_equal(v, ov)
+    s.close()
+
+
+def test_config1_8192_properties(gpu):
+    n = 8192
+    I0, I1 = synth.make_pair(n, n, seed=7, shear=4.0 / n)
+    kw = dict(lambda_=0.15, nscales=6, inner_iterations=30, outer_iterations=10)
+    s = gpu.Solver(gpu.default_params(**kw))
+    u, v = s.calc(I0, I1)
+    it_fused = s.stats.iters_array().copy()
+    assert s.stats.levels == 6
+    # (1) same handle, same inputs: identical
+    u2, v2 = s.calc(I0, I1)
+    assert np.array_equal(u, u2) and np.array_equal(v, v2)
+    assert np.array_equal(it_fused, s.stats.iters_array())
+    # (2) one iteration per launch everywhere: identical to the temporally blocked schedule
+    s.set_option("fused_min_px", 1e18)
+    u3, v3 = s.calc(I0, I1)
+    assert np.array_equal(it_fused, s.stats.iters_array())
+    assert np.array_equal(u, u3) and np.array_equal(v, v3)
+    del u2, v2, u3, v3
+    # (3) the known displacement is recovered (margins: the border has no data to match)
+    ut, vt = synth.true_flow(n, n, shear=4.0 / n)
+    epe = np.hypot(u - ut, v - vt)
+    assert epe.mean() < 0.08
+    assert epe[16:-16, 16:-16].max() < 0.5
+    # (4) the stop test really decided: every (level, warp) ended before the iteration cap
+    assert it_fused.max() < 300 and it_fused.min() >= 1
+    s.close()
+
+
+def test_config1_crop_matches_oracle_interior(gpu, orc):
+    """The finest levels of an 8192^2 solve and of a solve of its centre crop see the same data
+    away from the crop border, so there the two flows agree closely: a loose, size-independent
+    tie between the full-size CUDA result and the CPU oracle (which only runs the crop)."""
+    n, c = 8192, 1024
+    I0, I1 = synth.make_pair(n, n, seed=7, shear=4.0 / n)
+    s = gpu.Solver(gpu.default_params(lambda_=0.15, nscales=6))
+    u, v = s.calc(I0, I1)
+    o = (n - c) // 2
+    ou, ov, _, _ = orc.tvl1_calc(I0[o:o + c, o:o + c], I1[o:o + c, o:o + c], **{"lambda": 0.15, "nscales": 6})
+    m = 128
+    du = u[o + m:o + c - m, o + m:o + c - m] - ou[m:-m, m:-m]
+    dv = v[o + m:o + c - m, o + m:o + c - m] - ov[m:-m, m:-m]
+    epe = np.hypot(du, dv)
+    assert epe.mean() < 0.02, epe.mean()
+    s.close()
+
+
+def test_config3_large_displacement_exact(gpu, orc):
+    h = w = 768
+    I0, I1 = synth.make_pair(h, w, seed=13, dx=13.4, dy=-9.2, shear=0.008, margin=64)
+    kw = {"lambda": 0.15, "nscales": 8, "warps": 10}
+    s = gpu.Solver(gpu.default_params(lambda_=0.15, nscales=8, warps=10))
+    u, v = s.calc(I0, I1)
+    ou, ov, oit, olev = orc.tvl1_calc(I0, I1, **kw)
+    assert s.stats.levels == olev
+    assert np.array_equal(s.stats.iters_array(), oit[:olev])
+    assert np.array_equal(u, ou) and np.array_equal(v, ov)
+    s.close()
