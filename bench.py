@@ -13,8 +13,9 @@ One JSON line on stdout (rank 0):
   value     Mpx/s with the frames already resident in HBM (tvl1_calc_u8, CUDA events)
   e2e       Mpx/s through the host-buffer C-ABI call (tvl1_calc_u8_host): H2D of both frames
             from pinned memory and D2H of both flow planes inside the timed region
-  roofline  the primal-dual iteration kernel (k_iterate): 64 B/px/iteration
-            x the px-iterations it executed / its CUDA-event time inside the timed region
+  roofline  the primal-dual iteration kernels (k_iterate2: two iterations per launch, k_iterate: one):
+            64 B/px/iteration x the px-iterations executed / their CUDA-event time
+            inside the timed region (no-op launches and host read-backs of the stop flag included)
   cpu_baseline  the C oracle (oracle/, OpenMP) on a bounded crop of the same pair
 """
 import argparse
@@ -328,11 +329,13 @@ def run_ours(args):
                 per_level.append({"level": l, "size": [w, h],
                                   "gbs": round(64.0 * lvl_pxit[l] / (lvl_ms[l] * 1e-3) / 1e9, 1),
                                   "ms": round(lvl_ms[l] / K, 3)})
-        traffic = None
+        traffic = traffic_kernel = None
         tp = os.path.join(ROOT, "profiles", "k_iterate_traffic.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+                tj = json.load(open(tp))
+                traffic = tj.get("dram_bytes_per_launch")
+                traffic_kernel = tj.get("kernel")
             except Exception:
                 traffic = None
         line = {
@@ -345,14 +348,17 @@ def run_ours(args):
                     "ms_per_step": ms_e2e / K, "api": "tvl1_calc_u8_host (pinned host buffers)",
                     "checksum": checksum},
             "gpu_launches": total_launches,
-            "roofline": {"bound": "hbm", "kernel": "k_iterate (all levels, inside the timed region)",
+            "roofline": {"bound": "hbm",
+                         "kernel": "k_iterate2 + k_iterate (primal-dual iterations, all levels, inside the timed region)",
                          "achieved": ach, "peak": peak, "unit": "GB/s",
                          "frac": ach / peak if peak else None, "traffic": traffic,
                          "peak_source": peak_src, "copy_gbs_this_box": copy_gbs,
                          "frac_of_this_box_copy": (ach / copy_gbs) if copy_gbs else None,
                          "bytes_per_px_iteration": 64,
                          "px_iterations_per_step": it_px / K, "kernel_ms_per_step": it_ms / K,
-                         "launch_bytes_level0": 64.0 * levels[0][0] * levels[0][1],
+                         "traffic_kernel": traffic_kernel,
+                         "launch_bytes_level0": 2 * 64.0 * levels[0][0] * levels[0][1],
+                         "launch_bytes_note": "k_iterate2 advances two iterations per launch: 128 B/px algorithmic",
                          "per_level": per_level,
                          "pair_algorithmic_gbs": alg_bytes / (ms_dev / K * 1e-3) / 1e9},
             "clocks": clocks,
