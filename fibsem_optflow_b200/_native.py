@@ -71,6 +71,7 @@ class StackIO(C.Structure):
 EXPORTS = [
     "tvl1_version", "tvl1_last_error", "tvl1_default_params", "tvl1_create", "tvl1_destroy",
     "tvl1_set_params", "tvl1_set_option", "tvl1_set_timing", "tvl1_calc_u8", "tvl1_calc_u8_host",
+    "tvl1_prescaled_size", "tvl1_prescale_u8", "tvl1_prescale_u8_host",
     "tvl1_mask_flow_u8", "tvl1_sample_matches", "tvl1_sample_matches_skip", "tvl1_stack_run", "tvl1_k_convert_u8", "tvl1_k_resize",
     "tvl1_k_centered_gradient", "tvl1_k_warp", "tvl1_k_iterate", "tvl1_k_iterate_fused2", "tvl1_k_median5", "tvl1_k_last_ms",
     "tvl1_pyramid_sizes", "tvl1_glibc_rand", "tvl1_selftest_arith", "tvl1_dev_count", "tvl1_dev_alloc", "tvl1_dev_free",
@@ -128,6 +129,9 @@ def lib():
     L.tvl1_k_iterate.argtypes = [_vp] * 10 + [C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
                                               C.c_float, C.c_int, _vp, _vp]
     L.tvl1_k_iterate_fused2.argtypes = L.tvl1_k_iterate.argtypes
+    L.tvl1_prescaled_size.argtypes = [C.c_int, C.c_int, C.c_double, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.tvl1_prescale_u8.argtypes = [_vp, _sz, C.c_int, C.c_int, C.c_double, _vp, _sz, _vp]
+    L.tvl1_prescale_u8_host.argtypes = [C.c_int, _vp, _sz, C.c_int, C.c_int, C.c_double, _vp, _sz]
     L.tvl1_k_median5.argtypes = [_vp, C.c_int, C.c_int, C.c_int, _vp, _vp]
     L.tvl1_k_last_ms.argtypes = [C.POINTER(C.c_float)]
     L.tvl1_pyramid_sizes.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, _vp, _vp]
@@ -180,6 +184,17 @@ def pyramid_sizes(w, h, nscales, scale_step):
     hs = (C.c_int * (MAX_LEVELS + 1))()
     n = check(lib().tvl1_pyramid_sizes(w, h, nscales, scale_step, ws, hs))
     return [(ws[i], hs[i]) for i in range(n)]
+
+
+def prescale_u8(src, scale, device=0):
+    """8-bit cv::resize(src, Size(), scale, scale) of the reference's loader, on the device."""
+    src = np.ascontiguousarray(src, np.uint8)
+    h, w = src.shape
+    dw, dh = C.c_int(0), C.c_int(0)
+    check(lib().tvl1_prescaled_size(w, h, float(scale), C.byref(dw), C.byref(dh)))
+    dst = np.empty((dh.value, dw.value), np.uint8)
+    check(lib().tvl1_prescale_u8_host(device, src.ctypes.data, w, w, h, float(scale), dst.ctypes.data, dw.value))
+    return dst
 
 
 def k_last_ms():

@@ -1008,6 +1008,56 @@ int tvl1_pyramid_sizes(int w, int h, int nscales, double scale_step, int* ws, in
     return pyramid_sizes(w, h, nscales, scale_step, ws, hs);
 }
 
+// ---- 8-bit prescale of the loader (reference src/optflow.cpp:111,124)
+
+static int scaled_size_i(int n, double f) { return (int)lrint((double)n * f); }   // cvRound
+
+int tvl1_prescaled_size(int w, int h, double scale, int* dw, int* dh)
+{
+    if (!dw || !dh || w <= 0 || h <= 0 || !(scale > 0.0)) return fail(TVL1_ERR_INVALID, "bad argument");
+    *dw = scaled_size_i(w, scale);
+    *dh = scaled_size_i(h, scale);
+    if (*dw <= 0 || *dh <= 0) return fail(TVL1_ERR_INVALID, "scale %g leaves no pixels of %dx%d", scale, w, h);
+    return TVL1_OK;
+}
+
+int tvl1_prescale_u8(const uint8_t* d_src, size_t spitch, int w, int h, double scale, uint8_t* d_dst, size_t dpitch,
+                     void* stream)
+{
+    int dw = 0, dh = 0;
+    int rc = tvl1_prescaled_size(w, h, scale, &dw, &dh);
+    if (rc) return rc;
+    if (!d_src || !d_dst || spitch < (size_t)w || dpitch < (size_t)dw) return fail(TVL1_ERR_INVALID, "bad buffer or pitch");
+    cudaStream_t st = (cudaStream_t)stream;
+    dim3 b(32, 8);
+    const double inv = 1.0 / scale;
+    if (inv == 2.0) k_prescale_half_u8<<<grid2d(dw, dh, b), b, 0, st>>>(d_src, spitch, w, h, d_dst, dpitch, dw, dh);
+    else k_prescale_u8<<<grid2d(dw, dh, b), b, 0, st>>>(d_src, spitch, w, h, inv, d_dst, dpitch, dw, dh);
+    CK(cudaGetLastError());
+    return TVL1_OK;
+}
+
+int tvl1_prescale_u8_host(int device, const uint8_t* src, size_t spitch, int w, int h, double scale, uint8_t* dst,
+                          size_t dpitch)
+{
+    int dw = 0, dh = 0;
+    int rc = tvl1_prescaled_size(w, h, scale, &dw, &dh);
+    if (rc) return rc;
+    if (!src || !dst || spitch < (size_t)w || dpitch < (size_t)dw) return fail(TVL1_ERR_INVALID, "bad buffer or pitch");
+    CK(cudaSetDevice(device));
+    uint8_t *ds = nullptr, *dd = nullptr;
+    CK(cudaMalloc(&ds, (size_t)w * h));
+    if (cudaMalloc(&dd, (size_t)dw * dh) != cudaSuccess) { cudaFree(ds); return fail(TVL1_ERR_CUDA, "cudaMalloc failed"); }
+    rc = TVL1_OK;
+    if (cudaMemcpy2D(ds, w, src, spitch, w, h, cudaMemcpyHostToDevice) != cudaSuccess) rc = fail(TVL1_ERR_CUDA, "upload failed");
+    if (!rc) rc = tvl1_prescale_u8(ds, w, w, h, scale, dd, dw, nullptr);
+    if (!rc && cudaMemcpy2D(dst, dpitch, dd, dw, dw, dh, cudaMemcpyDeviceToHost) != cudaSuccess)
+        rc = fail(TVL1_ERR_CUDA, "download failed: %s", cudaGetErrorString(cudaGetLastError()));
+    cudaFree(ds);
+    cudaFree(dd);
+    return rc;
+}
+
 // ---- device-memory helpers
 
 int tvl1_dev_count(void)

@@ -236,21 +236,6 @@ inline bool read_gray8(const std::string& path, Gray8& img, std::string& err)
     return false;
 }
 
-// cv::resize(img, Size(), 0.5, 0.5) on 8-bit data: OpenCV takes its INTER_AREA fast path for an
-// exact 2x decimation, (a+b+c+d+2)>>2.  Even sizes only.
-inline bool half_scale(const Gray8& in, Gray8& out, std::string& err)
-{
-    if ((in.w | in.h) & 1) { err = "scale 0.5 needs even image sizes"; return false; }
-    out.w = in.w / 2; out.h = in.h / 2;
-    out.px.resize((size_t)out.w * out.h);
-    for (int y = 0; y < out.h; y++) {
-        const uint8_t* a = &in.px[(size_t)(2 * y) * in.w];
-        const uint8_t* b = a + in.w;
-        uint8_t* o = &out.px[(size_t)y * out.w];
-        for (int x = 0; x < out.w; x++) o[x] = (uint8_t)((a[2 * x] + a[2 * x + 1] + b[2 * x] + b[2 * x + 1] + 2) >> 2);
-    }
-    return true;
-}
 
 // ---- float TIFF writer -----------------------------------------------------------------------
 

@@ -16,7 +16,9 @@
 //     without the alignment the reference would force (:366);
 //   * match batches are written to <output_dir>/point_matches_<n>.json with exactly the payload
 //     upload_points would PUT to the Render service (:620-634) -- there is no network here;
-//   * `scale` must be 1 or 0.5 (the two values whose 8-bit cv::resize result is pinned).
+// N2: every decoded frame is prescaled by `scale` on the device (tvl1_prescale_u8_host: the 8-bit
+// cv::resize of :111,124, bit for bit, any factor), and the NEXT pair's frames are decoded on a host
+// thread while the current pair is solved.
 // All arithmetic runs in libtvl1_b200.so; this file only moves bytes and JSON.
 #include <zlib.h>
 
@@ -25,7 +27,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <ctime>
+#include <future>
 #include <iostream>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -264,20 +268,31 @@ void upload_points(Driver& D, Value& args)
     }
 }
 
-bool load_frame(const std::string& path, float scale, imio::Gray8& out)
+// decode only (host thread safe: touches no CUDA state)
+struct Decoded { bool ok = false; std::string err; imio::Gray8 img; };
+Decoded decode_frame(const std::string& path)
 {
-    imio::Gray8 raw;
-    std::string err;
-    if (!imio::read_gray8(path, raw, err)) {
-        std::cout << "Error: " << path << " (" << err << ")\n";
+    Decoded d;
+    d.ok = imio::read_gray8(path, d.img, d.err);
+    return d;
+}
+
+// cv::imread + cv::resize(frame, frame, Size(), scale, scale) of the reference (:106-111, :119-124);
+// the resize runs on the device
+bool finish_frame(int device, const std::string& path, Decoded&& d, float scale, imio::Gray8& out)
+{
+    if (!d.ok) {
+        std::cout << "Error: " << path << " (" << d.err << ")\n";
         return false;
     }
-    if (scale == 1.f) { out = std::move(raw); return true; }
-    if (scale == 0.5f) {
-        if (!imio::half_scale(raw, out, err)) { std::cout << "Error: " << path << " (" << err << ")\n"; return false; }
-        return true;
-    }
-    die("scale must be 1 or 0.5 (other factors of the 8-bit cv::resize are not restated)");
+    if (scale == 1.f) { out = std::move(d.img); return true; }
+    int dw = 0, dh = 0;
+    ck(tvl1_prescaled_size(d.img.w, d.img.h, (double)scale, &dw, &dh), "prescale");
+    out.w = dw; out.h = dh;
+    out.px.resize((size_t)dw * dh);
+    ck(tvl1_prescale_u8_host(device, d.img.px.data(), (size_t)d.img.w, d.img.w, d.img.h, (double)scale, out.px.data(),
+                             (size_t)dw), "prescale");
+    return true;
 }
 
 // solve_rois (src/optflow.cpp:312-392)
@@ -320,6 +335,10 @@ int from_file(Driver& D, Value& args, int shard, int nshards)
     Cached cache[2];
     long long last_upload = 0;
     bool any_upload_since = false;
+    std::map<std::string, std::future<Decoded>> inflight;   // frames being decoded for the next pair
+    auto prefetch = [&](const std::string& name) {
+        if (!inflight.count(name)) inflight.emplace(name, std::async(std::launch::async, decode_frame, name));
+    };
     const size_t n = images.size();
     const size_t base = n / nshards, rem = n % nshards;
     const size_t begin = shard * base + std::min<size_t>(shard, rem), end = begin + base + ((size_t)shard < rem ? 1 : 0);
@@ -333,9 +352,24 @@ int from_file(Driver& D, Value& args, int shard, int nshards)
         auto fetch = [&](const std::string& name, imio::Gray8& out) -> bool {
             for (Cached& c : cache)
                 if (c.name == name && c.scale == scale) { out = c.img; return true; }
-            return load_frame(name, scale, out);
+            Decoded d;
+            auto it = inflight.find(name);
+            if (it != inflight.end()) { d = it->second.get(); inflight.erase(it); }
+            else d = decode_frame(name);
+            return finish_frame(D.device, name, std::move(d), scale, out);
         };
-        if (!fetch(n0, frame0) || !fetch(n1, frame1)) continue;
+        const bool have = fetch(n0, frame0) && fetch(n1, frame1);
+        // decode what the next pair will need while this one is solved (a slice shared with this
+        // pair comes out of the cache instead)
+        if (i + 1 < end) {
+            const Value& nx = images[i + 1];
+            if (nx.isMember("p") && nx.isMember("q")) {
+                const std::string m0 = nx.at("p").asString(), m1 = nx.at("q").asString();
+                if (m0 != n0 && m0 != n1) prefetch(m0);
+                if (m1 != n0 && m1 != n1 && m1 != m0) prefetch(m1);
+            }
+        }
+        if (!have) continue;
         cache[0].name = n0; cache[0].scale = scale; cache[0].img = frame0;
         cache[1].name = n1; cache[1].scale = scale; cache[1].img = frame1;
 

@@ -168,6 +168,18 @@ typedef struct tvl1_stack_io {
 
 int tvl1_stack_run(tvl1_handle* h, const tvl1_stack_io* io, float* ms_total);
 
+/* ---- 8-bit prescale: the reference's loader shrinks every decoded frame with
+ * cv::resize(frame, frame, cv::Size(), scale, scale) before anything else (src/optflow.cpp:111,124;
+ * `scale` is a float job key, default 0.5).  Same result bit for bit (OpenCV's 11-bit fixed-point
+ * bilinear, its 2x2 area path for scale == 0.5), computed on the device.  Output size:
+ * cvRound(w * scale) x cvRound(h * scale).  Pitches in bytes. ---- */
+int tvl1_prescaled_size(int w, int h, double scale, int* dw, int* dh);
+int tvl1_prescale_u8(const uint8_t* d_src, size_t spitch, int w, int h, double scale,
+                     uint8_t* d_dst, size_t dpitch, void* stream);
+/* host buffers: upload, prescale, download (blocking; scratch allocated per call) */
+int tvl1_prescale_u8_host(int device, const uint8_t* src, size_t spitch, int w, int h, double scale,
+                          uint8_t* dst, size_t dpitch);
+
 /* ---- stage-level entry points: the individual kernels, exposed so that each can be
  * checked against the oracle on its own (tests/) and profiled on its own (bench.py).
  * Planes are fp32 with a pitch in ELEMENTS; pointers are device memory. ---- */

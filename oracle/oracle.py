@@ -64,6 +64,8 @@ def lib():
     L.orc_tvl1_calc.argtypes = [C.POINTER(OrcParams), _u8p, C.c_long, _u8p, C.c_long, C.c_int,
                                 C.c_int, _f32p, _f32p, C.c_void_p]
     L.orc_tvl1_calc.restype = C.c_int
+    L.orc_prescale_u8.argtypes = [_u8p, C.c_long, C.c_int, C.c_int, C.c_double, _u8p, C.c_long, C.c_int, C.c_int]
+    L.orc_prescale_u8.restype = None
     L.orc_mask_flow.argtypes = [_u8p, C.c_long, C.c_int, C.c_int, _f32p, _f32p]
     L.orc_random_points.argtypes = [_u8p, C.c_long, _u8p, C.c_long, _f32p, _f32p, C.c_int, C.c_int,
                                     C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int,
@@ -174,6 +176,16 @@ def tvl1_calc(I0, I1, params=None, **kw):
     if n < 0:
         raise RuntimeError("orc_tvl1_calc failed: %d" % n)
     return u, v, iters, n
+
+
+def prescale_u8(src, scale):
+    """8-bit cv::resize(src, Size(), scale, scale) of the reference's loader (src/optflow.cpp:111,124)."""
+    src = np.ascontiguousarray(src, np.uint8)
+    h, w = src.shape
+    dw, dh = scaled_size(w, scale), scaled_size(h, scale)
+    dst = np.empty((dh, dw), np.uint8)
+    lib().orc_prescale_u8(src, w, w, h, float(scale), dst, dw, dw, dh)
+    return dst
 
 
 def mask_flow(f1, u, v):

@@ -641,6 +641,70 @@ int orc_tvl1_calc(const orc_params* p, const unsigned char* I0, long pitch0,
     return nscales;
 }
 
+/* ------------------------------------------------------- wrapper: 8-bit prescale */
+
+/* cv::resize(frame, frame, cv::Size(), scale, scale) on the decoded 8-bit frame (reference
+ * src/optflow.cpp:111,124; default INTER_LINEAR).  OpenCV's 8-bit bilinear path works in fixed
+ * point: 11-bit coefficients cvRound((1-f)*2048), cvRound(f*2048), horizontal pass in int, vertical
+ * pass ((b0*(r0>>4))>>16) + ((b1*(r1>>4))>>16), then (+2)>>2.  The column fraction is clamped at
+ * the image border, the row fraction is not (only the row index is).  A decimation by exactly 2
+ * takes the 2x2 area path instead: (a+b+c+d+2)>>2, and where the source ends early the mean of the
+ * pixels that exist, cvRound((float)sum/count).  Pinned bit-exactly against cv2.resize
+ * (tests/golden/prescale.npz). */
+void orc_prescale_u8(const unsigned char* src, long spitch, int w, int h, double scale,
+                     unsigned char* dst, long dpitch, int dw, int dh)
+{
+    const double inv = 1.0 / scale;
+    if (inv == 2.0) {
+        const int dw1 = w / 2;
+        for (int dy = 0; dy < dh; dy++) {
+            const int sy0 = dy * 2;
+            const int wfast = sy0 + 2 <= h ? dw1 : 0;
+            for (int dx = 0; dx < dw; dx++) {
+                const int sx0 = dx * 2;
+                unsigned char o = 0;
+                if (dx < wfast) {
+                    const unsigned char* a = src + (size_t)sy0 * spitch + sx0;
+                    o = (unsigned char)((a[0] + a[1] + a[spitch] + a[spitch + 1] + 2) >> 2);
+                } else if (sx0 < w && sy0 < h) {
+                    int sum = 0, count = 0;
+                    for (int yy = 0; yy < 2 && sy0 + yy < h; yy++)
+                        for (int xx = 0; xx < 2 && sx0 + xx < w; xx++) {
+                            sum += src[(size_t)(sy0 + yy) * spitch + sx0 + xx];
+                            count++;
+                        }
+                    o = (unsigned char)cv_round_f((float)sum / (float)count);
+                }
+                dst[(size_t)dy * dpitch + dx] = o;
+            }
+        }
+        return;
+    }
+    for (int dy = 0; dy < dh; dy++) {
+        float fy = (float)(((double)dy + 0.5) * inv - 0.5);
+        const int sy = (int)floorf(fy);
+        fy -= (float)sy;
+        const int b0 = cv_round_f((1.f - fy) * 2048.f), b1 = cv_round_f(fy * 2048.f);
+        const int r0 = sy < 0 ? 0 : (sy > h - 1 ? h - 1 : sy);
+        const int r1 = sy + 1 < 0 ? 0 : (sy + 1 > h - 1 ? h - 1 : sy + 1);
+        const unsigned char* S0 = src + (size_t)r0 * spitch;
+        const unsigned char* S1 = src + (size_t)r1 * spitch;
+        for (int dx = 0; dx < dw; dx++) {
+            float fx = (float)(((double)dx + 0.5) * inv - 0.5);
+            int sx = (int)floorf(fx);
+            fx -= (float)sx;
+            if (sx < 0) { fx = 0.f; sx = 0; }
+            if (sx >= w - 1) { fx = 0.f; sx = w - 1; }
+            const int a0 = cv_round_f((1.f - fx) * 2048.f), a1 = cv_round_f(fx * 2048.f);
+            const int sx1 = sx + 1 > w - 1 ? w - 1 : sx + 1;
+            const int h0 = S0[sx] * a0 + S0[sx1] * a1;
+            const int h1 = S1[sx] * a0 + S1[sx1] * a1;
+            int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+            dst[(size_t)dy * dpitch + dx] = (unsigned char)(v < 0 ? 0 : (v > 255 ? 255 : v));
+        }
+    }
+}
+
 /* ------------------------------------------------------- wrapper: mask, sample */
 
 void orc_mask_flow(const unsigned char* f1, long pitch1, int w, int h, float* u, float* v)

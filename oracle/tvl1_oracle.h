@@ -87,6 +87,11 @@ int orc_tvl1_calc(const orc_params* p, const unsigned char* I0, long pitch0,
                   const unsigned char* I1, long pitch1, int w, int h,
                   float* u, float* v, int* iters_out);
 
+/* reference src/optflow.cpp:111,124: cv::resize(frame, frame, Size(), scale, scale) on the 8-bit frame.
+ * dw, dh = orc_scaled_size(w, scale), orc_scaled_size(h, scale). */
+void orc_prescale_u8(const unsigned char* src, long spitch, int w, int h, double scale,
+                     unsigned char* dst, long dpitch, int dw, int dh);
+
 /* reference src/optflow.cpp:471-473: flow = 0 where frame1 <= 1 */
 void orc_mask_flow(const unsigned char* f1, long pitch1, int w, int h, float* u, float* v);
 

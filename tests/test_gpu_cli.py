@@ -130,3 +130,30 @@ def test_cli_rejects(gpu, tmp_path):
     assert subprocess.call([exe, jf], stderr=subprocess.DEVNULL) != 0
     open(jf, "w").write('{"images": [ {"p": "x" "q": "y"} ]}')     # missing comma, like docs/example.json:72
     assert subprocess.call([exe, jf], stderr=subprocess.DEVNULL) != 0
+
+
+def test_general_scale_and_prefetch(gpu, orc, tmp_path):
+    """N2: any `scale` (prescaled on the device exactly like the loader's 8-bit cv::resize), frames of
+    the next pair decoded on a host thread; three unrelated pairs so that nothing comes from the cache."""
+    exe = build_cli()
+    sl = synth.make_stack(5, 200, 260, seed=33)
+    names = []
+    for k, a in enumerate(sl):
+        p = str(tmp_path / ("g%d.png" % k))
+        write_png(p, a)
+        names.append(p)
+    pairs = [(0, 1), (2, 3), (4, 5)]
+    job = {"debug": True, "output_type": "flow", "scale": 0.3, "lambda": 0.15, "nscales": 3, "output_dir": str(tmp_path),
+           "images": [{"p": names[a], "q": names[b], "output_name": "p%d" % a} for a, b in pairs]}
+    jf = str(tmp_path / "job.json")
+    json.dump(job, open(jf, "w"))
+    subprocess.check_call([exe, jf], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    scf = float(np.float32(0.3))
+    for a, b in pairs:
+        f0, f1 = orc.prescale_u8(sl[a], scf), orc.prescale_u8(sl[b], scf)
+        ou, ov, _, _ = orc.tvl1_calc(f0, f1, **{"lambda": 0.15, "nscales": 3})
+        ou = np.where(f1 <= 1, np.float32(0), ou)
+        ov = np.where(f1 <= 1, np.float32(0), ov)
+        base = str(tmp_path / ("p%d_0.30" % a))
+        assert np.array_equal(read_tiff_f32(base + "_x.tiff"), ou)
+        assert np.array_equal(read_tiff_f32(base + "_y.tiff"), ov)

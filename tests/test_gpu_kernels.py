@@ -107,3 +107,20 @@ def test_iterate_fused2(gpu, orc, h, w, n):
     for k in range(6):
         assert np.array_equal(got[k], want[k]), names[k]
     np.testing.assert_allclose(got[6], werr, rtol=1e-12)
+
+
+def test_prescale_u8(gpu, orc):
+    """tvl1_prescale_u8: the loader's 8-bit cv::resize on the device -- cv2-made golden vectors and,
+    at a realistic size, the oracle."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "prescale.npz"))
+    for k in range(int(g["n"])):
+        got = gpu.prescale_u8(g["src_%d" % k], float(g["scale_%d" % k]))
+        assert got.shape == g["dst_%d" % k].shape and np.array_equal(got, g["dst_%d" % k]), k
+    rng = np.random.default_rng(8)
+    src = rng.integers(0, 256, size=(1531, 2049), dtype=np.uint8)
+    for sc in (0.5, 0.37, 0.25, 0.9):
+        scf = float(np.float32(sc))
+        assert np.array_equal(gpu.prescale_u8(src, scf), orc.prescale_u8(src, scf)), sc
+    with pytest.raises(gpu.Tvl1Error):
+        gpu.prescale_u8(src[:4, :4], 0.01)

@@ -185,3 +185,13 @@ def test_iterate_vs_numpy(orc):
     for k in range(6):
         assert np.array_equal(got[k], want[k])
     assert abs(err - want[6]) <= 1e-12 * abs(err)
+
+
+def test_prescale_golden(orc):
+    """8-bit cv::resize of the reference's loader (src/optflow.cpp:111,124) against cv2-made vectors:
+    0.5 (area path, odd sizes included) and general factors (11-bit fixed-point bilinear)."""
+    g = np.load(os.path.join(GOLD, "prescale.npz"))
+    assert int(g["n"]) >= 30
+    for k in range(int(g["n"])):
+        got = orc.prescale_u8(g["src_%d" % k], float(g["scale_%d" % k]))
+        assert got.shape == g["dst_%d" % k].shape and np.array_equal(got, g["dst_%d" % k]), k
