@@ -63,7 +63,7 @@ class StackIO(C.Structure):
         ("h_u", C.POINTER(C.c_void_p)), ("h_v", C.POINTER(C.c_void_p)), ("pitch_out", C.c_size_t),
         ("npoints", C.c_int), ("scale", C.c_float), ("seed", C.c_longlong),
         ("px", C.c_void_p), ("py", C.c_void_p), ("qx", C.c_void_p), ("qy", C.c_void_p), ("w", C.c_void_p),
-        ("n_out", C.c_void_p), ("stats", C.POINTER(Stats)),
+        ("n_out", C.c_void_p), ("stats", C.POINTER(Stats)), ("prescale", C.c_double),
     ]
 
 
@@ -347,7 +347,7 @@ class Solver:
         return px[:k], py[:k], qx[:k], qy[:k], wg[:k], pos[:k]
 
     def run_stack(self, slices, flows=True, apply_mask=False, npoints=-1, scale=0.5, seed=-1,
-                  out_u=None, out_v=None, slice_ptrs=None, pitch=None, shape=None):
+                  out_u=None, out_v=None, slice_ptrs=None, pitch=None, shape=None, prescale=0.0):
         """Pairs (k, k+1) of a stack of uint8 slices (tvl1_stack_run).  Returns a dict with
         'u', 'v' (lists of planes, if flows), 'matches' (per pair px,py,qx,qy,w, if npoints >= 0),
         'stats' (per pair), 'ms' (CUDA-event time of the whole stack).  slice_ptrs/out_u/out_v let
@@ -367,6 +367,11 @@ class Solver:
         io.pitch = pitch
         io.n_slices, io.width, io.height = n, w, h
         io.apply_mask = int(bool(apply_mask))
+        io.prescale = float(prescale)
+        if prescale not in (0.0, 1.0):   # the flow planes have the prescaled size
+            dw, dh = C.c_int(0), C.c_int(0)
+            check(lib().tvl1_prescaled_size(w, h, float(prescale), C.byref(dw), C.byref(dh)))
+            w, h = dw.value, dh.value
         us = vs = None
         if flows:
             if out_u is None:

@@ -263,6 +263,8 @@ struct tvl1_handle {
     void* samp = nullptr;
     // stack runner (tvl1_stack_run): 3 slice slots, 2 flow buffers, copy streams
     uint8_t* st_slice[3] = {nullptr, nullptr, nullptr};
+    uint8_t* st_raw[2] = {nullptr, nullptr};   // raw slices awaiting the device prescale
+    size_t st_raw_bytes = 0;
     float* st_flow[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
     size_t st_pitch8 = 0;
     int st_w = 0, st_h = 0;
@@ -655,6 +657,7 @@ void tvl1_destroy(tvl1_handle* H)
     if (H->d_vo) cudaFree(H->d_vo);
     tvl1::sampler_release(H->samp);
     for (int i = 0; i < 3; i++) { if (H->st_slice[i]) cudaFree(H->st_slice[i]); if (H->st_up[i]) cudaEventDestroy(H->st_up[i]); }
+    for (int i = 0; i < 2; i++) if (H->st_raw[i]) cudaFree(H->st_raw[i]);
     for (int i = 0; i < 2; i++) {
         for (int j = 0; j < 2; j++) if (H->st_flow[i][j]) cudaFree(H->st_flow[i][j]);
         if (H->st_ready[i]) cudaEventDestroy(H->st_ready[i]);
@@ -773,9 +776,13 @@ static int stack_reserve(tvl1_handle* H, int w, int h)
 int tvl1_stack_run(tvl1_handle* H, const tvl1_stack_io* io, float* ms_total)
 {
     if (!H || !io) return fail(TVL1_ERR_INVALID, "null handle or io");
-    const int w = io->width, h = io->height, n = io->n_slices;
-    if (!io->h_slices || n < 2 || w <= 0 || h <= 0 || io->pitch < (size_t)w)
+    const int n = io->n_slices;
+    const int rw = io->width, rh = io->height;          // size of the slices as given
+    int w = rw, h = rh;                                 // size the solver works at
+    const bool pre = io->prescale > 0.0 && io->prescale != 1.0;
+    if (!io->h_slices || n < 2 || rw <= 0 || rh <= 0 || io->pitch < (size_t)rw)
         return fail(TVL1_ERR_INVALID, "a stack needs >= 2 slices of non-zero size");
+    if (pre) { int r = tvl1_prescaled_size(rw, rh, io->prescale, &w, &h); if (r) return r; }
     if ((io->h_u == nullptr) != (io->h_v == nullptr)) return fail(TVL1_ERR_INVALID, "h_u and h_v go together");
     if (io->h_u && io->pitch_out < (size_t)w * 4) return fail(TVL1_ERR_INVALID, "pitch_out smaller than a row");
     if (io->npoints >= 0 && (!io->px || !io->py || !io->qx || !io->qy || !io->w || !io->n_out))
@@ -784,6 +791,15 @@ int tvl1_stack_run(tvl1_handle* H, const tvl1_stack_io* io, float* ms_total)
     CK(cudaSetDevice(H->device));
     int rc = stack_reserve(H, w, h);
     if (rc) return rc;
+    if (pre && H->st_raw_bytes < (size_t)rw * rh) {
+        for (int i = 0; i < 2; i++) {
+            if (H->st_raw[i]) cudaFree(H->st_raw[i]);
+            H->st_raw[i] = nullptr;
+        }
+        H->st_raw_bytes = 0;
+        for (int i = 0; i < 2; i++) CK(cudaMalloc(&H->st_raw[i], (size_t)rw * rh));
+        H->st_raw_bytes = (size_t)rw * rh;
+    }
     cudaStream_t cs = H->own_stream;
     const size_t p8 = H->st_pitch8;
     const int cap = io->npoints > 0 ? io->npoints : 1;
@@ -793,7 +809,17 @@ int tvl1_stack_run(tvl1_handle* H, const tvl1_stack_io* io, float* ms_total)
     CK(cudaEventRecord(t0, cs));
     auto upload = [&](int k) -> int {
         const int s = k % 3;
-        CK(cudaMemcpy2DAsync(H->st_slice[s], p8, io->h_slices[k], io->pitch, w, h, cudaMemcpyHostToDevice, H->st_in));
+        if (!pre) {
+            CK(cudaMemcpy2DAsync(H->st_slice[s], p8, io->h_slices[k], io->pitch, w, h, cudaMemcpyHostToDevice, H->st_in));
+        } else {
+            // raw slice -> device, then the loader's 8-bit resize (src/optflow.cpp:111,124) on the
+            // copy stream: the solver never sees the raw size.  Two staging buffers, re-used in stream
+            // order (slice k+2's upload follows slice k's prescale on the same stream)
+            uint8_t* raw = H->st_raw[k & 1];
+            CK(cudaMemcpy2DAsync(raw, (size_t)rw, io->h_slices[k], io->pitch, rw, rh, cudaMemcpyHostToDevice, H->st_in));
+            int r = tvl1_prescale_u8(raw, (size_t)rw, rw, rh, io->prescale, H->st_slice[s], p8, H->st_in);
+            if (r) return r;
+        }
         CK(cudaEventRecord(H->st_up[s], H->st_in));
         return TVL1_OK;
     };

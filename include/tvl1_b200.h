@@ -164,6 +164,11 @@ typedef struct tvl1_stack_io {
     double *px, *py, *qx, *qy, *w;    /* [(n_slices-1) * max(npoints,1)], or NULL if npoints < 0 */
     int* n_out;                       /* [n_slices-1] entries written per pair */
     tvl1_stats* stats;                /* [n_slices-1] or NULL */
+    double prescale;                  /* 0 or 1: slices are used as given.  Otherwise every slice is
+                                         shrunk on the device by this factor right after its upload,
+                                         exactly like the loader's cv::resize (src/optflow.cpp:111,124);
+                                         width/height/pitch describe the slices as given, the flow
+                                         planes have tvl1_prescaled_size(width, height, prescale) */
 } tvl1_stack_io;
 
 int tvl1_stack_run(tvl1_handle* h, const tvl1_stack_io* io, float* ms_total);

@@ -56,3 +56,23 @@ def test_stack_no_flow_download(gpu):
     assert "u" not in res and len(res["matches"]) == 2 and len(res["matches"][0][0]) == 25
     with pytest.raises(gpu.Tvl1Error):
         s.run_stack(slices[:1])
+
+
+@pytest.mark.parametrize("scale", [0.5, 0.4])
+def test_stack_prescale_on_device(gpu, orc, scale):
+    """Raw slices in, the loader's 8-bit cv::resize (src/optflow.cpp:111,124) applied on the device on
+    the copy stream: flows and matches equal the oracle's on slices it shrank itself."""
+    slices = synth.make_stack(3, 161, 230, seed=5)        # odd height: exercises the area path's border rule
+    scf = float(np.float32(scale))
+    small = [orc.prescale_u8(a, scf) for a in slices]
+    s = gpu.Solver(gpu.default_params(lambda_=0.15, nscales=3))
+    res = s.run_stack(slices, flows=True, apply_mask=True, npoints=9, scale=scale, seed=3, prescale=scf)
+    for k in range(3):
+        ou, ov, oit, lev = orc.tvl1_calc(small[k], small[k + 1], **{"lambda": 0.15, "nscales": 3})
+        orc.mask_flow(small[k + 1], ou, ov)
+        assert res["u"][k].shape == ou.shape
+        assert np.array_equal(res["u"][k], ou) and np.array_equal(res["v"][k], ov)
+        want = orc.random_points(small[k], small[k + 1], ou, ov, scale=scale, npoints=9, seed=3)
+        for j in range(5):
+            assert np.array_equal(res["matches"][k][j], want[j])
+    s.close()
