@@ -136,7 +136,7 @@ def lib():
     L.tvl1_k_last_ms.argtypes = [C.POINTER(C.c_float)]
     L.tvl1_pyramid_sizes.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, _vp, _vp]
     L.tvl1_glibc_rand.argtypes = [C.c_longlong, C.c_longlong, C.c_int, _vp]
-    L.tvl1_selftest_arith.argtypes = [C.c_longlong, C.c_uint, C.c_int, C.c_int, C.POINTER(C.c_longlong)]
+    L.tvl1_selftest_arith.argtypes = [C.c_longlong, C.c_uint, C.c_int, C.c_int, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
     L.tvl1_dev_alloc.argtypes = [C.c_int, _sz, C.POINTER(_vp)]
     L.tvl1_dev_free.argtypes = [C.c_int, _vp]
     L.tvl1_dev_memset.argtypes = [_vp, C.c_int, _sz]
@@ -203,10 +203,10 @@ def k_last_ms():
     return ms.value
 
 
-def selftest_arith(n, seed=1, elo=-30, ehi=30):
-    bad = C.c_longlong(-1)
-    check(lib().tvl1_selftest_arith(n, seed, elo, ehi, C.byref(bad)))
-    return bad.value
+def selftest_arith(n, seed=1, elo=-30, ehi=30, with_unvouched=False):
+    bad, unv = C.c_longlong(-1), C.c_longlong(-1)
+    check(lib().tvl1_selftest_arith(n, seed, elo, ehi, C.byref(bad), C.byref(unv)))
+    return (bad.value, unv.value) if with_unvouched else bad.value
 
 
 def glibc_rand(seed, skip, n):

@@ -1013,18 +1013,19 @@ int tvl1_k_median5(const float* d_src, int w, int h, int pitch, float* d_dst, vo
     return rc;
 }
 
-int tvl1_selftest_arith(long long n, unsigned seed, int elo, int ehi, long long* mismatches)
+int tvl1_selftest_arith(long long n, unsigned seed, int elo, int ehi, long long* mismatches, long long* unvouched)
 {
     if (!mismatches || n <= 0 || elo > ehi || elo < -126 || ehi > 127) return fail(TVL1_ERR_INVALID, "bad argument");
     unsigned long long* d = nullptr;
-    CK(cudaMalloc(&d, sizeof(*d)));
-    cudaMemset(d, 0, sizeof(*d));
+    CK(cudaMalloc(&d, 2 * sizeof(*d)));
+    cudaMemset(d, 0, 2 * sizeof(*d));
     k_selftest_arith<<<148 * 8, 256>>>(seed, n, elo, ehi, d);
-    unsigned long long hres = 0;
-    cudaError_t e = cudaMemcpy(&hres, d, sizeof(hres), cudaMemcpyDeviceToHost);
+    unsigned long long hres[2] = {0, 0};
+    cudaError_t e = cudaMemcpy(hres, d, sizeof(hres), cudaMemcpyDeviceToHost);
     cudaFree(d);
     if (e != cudaSuccess) return fail(TVL1_ERR_CUDA, "selftest: %s", cudaGetErrorString(e));
-    *mismatches = (long long)hres;
+    *mismatches = (long long)hres[0];
+    if (unvouched) *unvouched = (long long)hres[1];
     return TVL1_OK;
 }
 

@@ -219,7 +219,8 @@ int tvl1_k_last_ms(float* ms);
 /* Self-test of the kernels' exact fast paths (reciprocal-sharing division, fused hypot) against
  * the IEEE operators on n pseudo-random operand triples with binary exponents in [elo, ehi];
  * *mismatches receives the number of differing results (must be 0). */
-int tvl1_selftest_arith(long long n, unsigned seed, int elo, int ehi, long long* mismatches);
+int tvl1_selftest_arith(long long n, unsigned seed, int elo, int ehi, long long* mismatches,
+                        long long* unvouched /* may be NULL: operand pairs the fp32 hypot handed to the exact path */);
 
 /* pyramid level sizes for (w, h): returns levels used (A.2 stop rule) */
 int tvl1_pyramid_sizes(int w, int h, int nscales, double scale_step, int* ws, int* hs);

@@ -86,7 +86,11 @@ def test_random_points_job(gpu, orc, tmp_path):
         p = str(tmp_path / ("t%d.png" % k))
         write_png(p, a)
         names.append(p)
-    job = {"debug": True, "output_type": "random_points", "scale": 1.0, "lambda": 0.15, "nscales": 3,
+    # top-level keys exactly as support_scripts/gen_cross_file_list.py:75-99 writes them (N3); the
+    # feature-matching knobs are carried along and ignored when "features" is absent
+    job = {"style": 1, "debug": True, "homo": 4, "ratio": 0.7, "ransac": 5, "hessianThreshold": 1600,
+           "host": "render.example.org", "port": 8080, "matchCollection": "test_v1", "owner": "flyem",
+           "output_type": "random_points", "scale": 1.0, "lambda": 0.15, "nscales": 3,
            "npoints": 7, "output_dir": str(tmp_path), "rois": {"top": 32, "bottom": 40},
            "images": [{"p": names[0], "q": names[1], "pId": "t0", "qId": "t1", "pGroupId": "1.0", "qGroupId": "2.0"},
                       {"p": names[1], "q": names[2], "pId": "t1", "qId": "t2", "pGroupId": "2.0", "qGroupId": "3.0",
@@ -96,6 +100,9 @@ def test_random_points_job(gpu, orc, tmp_path):
     subprocess.check_call([exe, jf], stdout=subprocess.DEVNULL)
     got = json.load(open(str(tmp_path / "point_matches_000.json")))
     assert [g["pId"] for g in got] == ["t0", "t1"] and got[1]["qGroupId"] == "3.0"
+    # the record move_pm builds (src/optflow.cpp:574-593), which upload_points PUTs to the Render service
+    assert all(set(g) == {"pGroupId", "pId", "qGroupId", "qId", "matches"} for g in got)
+    assert all(set(g["matches"]) == {"p", "q", "w"} for g in got)
     # the same job through the oracle, in a fresh process (unseeded rand() stream), ROI keys in
     # jsoncpp's alphabetical order: bottom, then top
     np.savez(str(tmp_path / "in.npz"), sl=np.stack(sl))
