@@ -118,7 +118,7 @@ int launch_gradient(const float* src, int w, int h, int pitch, float* dx, float*
 
 int launch_warp(const WarpArgs& a, cudaStream_t st)
 {
-    dim3 b(32, 8);
+    dim3 b(32, TVL1_WP_NW);
     dim3 g(cdiv(a.w, TVL1_WP_TW), cdiv(a.h, TVL1_WP_TH));
     k_warp<<<g, b, 0, st>>>(a);
     CK(cudaGetLastError());
