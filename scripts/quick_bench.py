@@ -6,6 +6,11 @@ from fibsem_optflow_b200 import _native as N, synth
 
 def run(h, w, nscales, reps=2):
     t = time.time(); I0, I1 = synth.make_pair(h, w, seed=7, shear=4.0/h); tg = time.time() - t
+    if os.environ.get("MASK_FRAC"):   # a zero band like the padding of aligned FIB-SEM frames
+        m = int(h * float(os.environ["MASK_FRAC"]))
+        I0 = I0.copy(); I1 = I1.copy()
+        I0[:m] = 0; I1[:m] = 0
+        I0[:, :m // 2] = 0; I1[:, :m // 2] = 0
     s = N.Solver(N.default_params(lambda_=0.15, nscales=nscales, inner_iterations=30, outer_iterations=10))
     if os.environ.get("FUSED_MIN_PX"):
         s.set_option("fused_min_px", float(os.environ["FUSED_MIN_PX"]))

@@ -99,3 +99,22 @@ def test_fused_schedule_is_exact(gpu, orc, h, w, seed, kw):
     assert np.array_equal(u, ou) and np.array_equal(v, ov)
     with pytest.raises(gpu.Tvl1Error):
         s.set_option("no_such_option", 1)
+
+
+def test_zero_padded_frames_exact(gpu, orc):
+    """Frames with exactly flat (zero) bands, like aligned FIB-SEM slices padded with zeros: inside the
+    bands the flow decays through tiny and subnormal values, which is where the kernels' fast
+    arithmetic has to hand over to (or provably agree with) the IEEE operators."""
+    I0, I1 = synth.make_pair(320, 384, seed=12)
+    I0 = I0.copy(); I1 = I1.copy()
+    I0[:90] = 0; I1[:96] = 0
+    I0[:, :70] = 0; I1[:, :64] = 0
+    I0[250:, 300:] = 0; I1[250:, 300:] = 0
+    for fused_min in (0, 1e18):
+        s = gpu.Solver(gpu.default_params(lambda_=0.15, nscales=4))
+        s.set_option("fused_min_px", fused_min)
+        u, v = s.calc(I0, I1)
+        ou, ov, oit, olev = orc.tvl1_calc(I0, I1, **{"lambda": 0.15, "nscales": 4})
+        assert np.array_equal(s.stats.iters_array(), oit[:olev])
+        assert np.array_equal(u, ou) and np.array_equal(v, ov)
+        s.close()
