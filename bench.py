@@ -358,7 +358,9 @@ def run_ours(args):
                          "px_iterations_per_step": it_px / K, "kernel_ms_per_step": it_ms / K,
                          "traffic_kernel": traffic_kernel,
                          "launch_bytes_level0": 2 * 64.0 * levels[0][0] * levels[0][1],
-                         "launch_bytes_note": "k_iterate2 advances two iterations per launch: 128 B/px algorithmic",
+                         "launch_bytes_note": "k_iterate2 advances two iterations per launch: 128 B/px algorithmic, "
+                                              "60 B/px compulsory (9 planes read + 6 written once); frac > 1 is what "
+                                              "temporal blocking is for -- `traffic` is the DRAM bytes ncu measured",
                          "per_level": per_level,
                          "pair_algorithmic_gbs": alg_bytes / (ms_dev / K * 1e-3) / 1e9},
             "clocks": clocks,
