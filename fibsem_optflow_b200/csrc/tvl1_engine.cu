@@ -95,17 +95,25 @@ int launch_convert(const uint8_t* src, size_t pitch, int w, int h, float* dst, i
     return TVL1_OK;
 }
 
-int launch_resize(const float* src, int sw, int sh, int sp, float* dst, int dw, int dh, int dp,
-                  double inv_scale, float mul, int apply_mul, cudaStream_t st)
+// one or two planes (srcB / dstB may be null) resized alike in one launch
+int launch_resize2(const float* srcA, const float* srcB, int sw, int sh, int sp, float* dstA, float* dstB, int dw, int dh,
+                   int dp, double inv_scale, float mul, int apply_mul, cudaStream_t st)
 {
     double inv_x, inv_y;
     if (inv_scale > 0) { inv_x = inv_scale; inv_y = inv_scale; }
     else { inv_x = (double)dw / sw; inv_y = (double)dh / sh; }
     const double scale_x = 1. / inv_x, scale_y = 1. / inv_y;
     dim3 b(32, 8);
-    k_resize<<<grid2d(dw, dh, b), b, 0, st>>>(src, sw, sh, sp, dst, dw, dh, dp, scale_x, scale_y, mul, apply_mul);
+    dim3 g(cdiv(cdiv(dw, 4), 32), cdiv(dh, 8), srcB ? 2 : 1);
+    k_resize<<<g, b, 0, st>>>(srcA, srcB, sw, sh, sp, dstA, dstB, dw, dh, dp, scale_x, scale_y, mul, apply_mul);
     CK(cudaGetLastError());
     return TVL1_OK;
+}
+
+int launch_resize(const float* src, int sw, int sh, int sp, float* dst, int dw, int dh, int dp,
+                  double inv_scale, float mul, int apply_mul, cudaStream_t st)
+{
+    return launch_resize2(src, nullptr, sw, sh, sp, dst, nullptr, dw, dh, dp, inv_scale, mul, apply_mul, st);
 }
 
 int launch_gradient(const float* src, int w, int h, int pitch, float* dx, float* dy, cudaStream_t st)
@@ -244,7 +252,7 @@ struct tvl1_handle {
     double cap_step = 0;
     int nlevels = 0;
     Level lv[TVL1_MAX_LEVELS];
-    float *I1x = nullptr, *I1y = nullptr, *I1wx = nullptr, *I1wy = nullptr, *grad = nullptr, *rho = nullptr;
+    float *I1wx = nullptr, *I1wy = nullptr, *rho = nullptr;   // warp outputs (I1x, I1y, grad never exist as planes)
     float *u1x = nullptr, *u2x = nullptr;   // twin [1] of u, shared by all levels
     float* p[4][2] = {{nullptr}};           // p11,p12,p21,p22 twins
     Ctrl* d_ctrl = nullptr;
@@ -315,8 +323,8 @@ static int ensure_capacity(tvl1_handle* H, int w, int h)
     }
     const int pitch0 = round_up(w, 32);
     const size_t b0 = (size_t)pitch0 * h * sizeof(float);
-    size_t o_scr[8], o_p[8];
-    for (int i = 0; i < 8; i++) o_scr[i] = carve(b0);   // I1x I1y I1wx I1wy grad rho u1x u2x
+    size_t o_scr[5], o_p[8];
+    for (int i = 0; i < 5; i++) o_scr[i] = carve(b0);   // I1wx I1wy rho u1x u2x
     for (int i = 0; i < 8; i++) o_p[i] = carve(b0);
     const size_t nb = iterate_max_blocks(w, h);
     const size_t o_part = carve(nb * sizeof(double));
@@ -334,8 +342,8 @@ static int ensure_capacity(tvl1_handle* H, int w, int h)
         H->lv[s].u1 = (float*)(H->arena + plan[s].u1); H->lv[s].u2 = (float*)(H->arena + plan[s].u2);
     }
     H->nlevels = L;
-    float** scr[8] = {&H->I1x, &H->I1y, &H->I1wx, &H->I1wy, &H->grad, &H->rho, &H->u1x, &H->u2x};
-    for (int i = 0; i < 8; i++) *scr[i] = (float*)(H->arena + o_scr[i]);
+    float** scr[5] = {&H->I1wx, &H->I1wy, &H->rho, &H->u1x, &H->u2x};
+    for (int i = 0; i < 5; i++) *scr[i] = (float*)(H->arena + o_scr[i]);
     for (int i = 0; i < 8; i++) H->p[i / 2][i % 2] = (float*)(H->arena + o_p[i]);
     H->d_partials = (double*)(H->arena + o_part);
     H->partials_cap = nb;
@@ -421,9 +429,8 @@ static int calc_device(tvl1_handle* H, const uint8_t* f0, size_t pitch0, const u
     launches += 2;
     for (int s = 1; s < L; s++) {
         const Level &a = H->lv[s - 1], &b = H->lv[s];
-        if ((rc = launch_resize(a.I0, a.w, a.h, a.pitch, b.I0, b.w, b.h, b.pitch, P.scale_step, 1.f, 0, st))) return rc;
-        if ((rc = launch_resize(a.I1, a.w, a.h, a.pitch, b.I1, b.w, b.h, b.pitch, P.scale_step, 1.f, 0, st))) return rc;
-        launches += 2;
+        if ((rc = launch_resize2(a.I0, a.I1, a.w, a.h, a.pitch, b.I0, b.I1, b.w, b.h, b.pitch, P.scale_step, 1.f, 0, st))) return rc;
+        launches += 1;
     }
     {
         const Level& c = H->lv[L - 1];
@@ -540,9 +547,9 @@ static int calc_device(tvl1_handle* H, const uint8_t* f0, size_t pitch0, const u
         const int uc = H->h_ctrl->ucur[s];
         const float mul = (float)(1 / P.scale_step);
         if ((rc = span_begin(3, s))) return rc;
-        if ((rc = launch_resize(uc ? H->u1x : lv.u1, lv.w, lv.h, lv.pitch, up.u1, up.w, up.h, up.pitch, 0.0, mul, 1, st))) return rc;
-        if ((rc = launch_resize(uc ? H->u2x : lv.u2, lv.w, lv.h, lv.pitch, up.u2, up.w, up.h, up.pitch, 0.0, mul, 1, st))) return rc;
-        launches += 2;
+        if ((rc = launch_resize2(uc ? H->u1x : lv.u1, uc ? H->u2x : lv.u2, lv.w, lv.h, lv.pitch, up.u1, up.u2, up.w, up.h,
+                                 up.pitch, 0.0, mul, 1, st))) return rc;
+        launches += 1;
         span_end();
     }
     // A.8: planar output
