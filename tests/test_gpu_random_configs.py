@@ -1,0 +1,52 @@
+"""Randomised parity: image sizes (odd, tiny, wide, tall), every solver parameter the reference's
+generate_TV_args exposes (src/optflow.cpp:500-514) plus scaleStep / inner / outer / medianFiltering, with
+and without zero bands, both iteration schedules -- each case bit-exact against the oracle, iteration
+counts included.  Seeds are fixed so that a failure reproduces."""
+import numpy as np
+import pytest
+
+from fibsem_optflow_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def draw(rng):
+    h = int(rng.integers(20, 420))
+    w = int(rng.integers(20, 520))
+    kw = dict(
+        tau=float(rng.choice([0.25, 0.2, 0.1, 0.3])),
+        lambda_=float(rng.choice([0.15, 0.05, 0.3, 0.6])),
+        theta=float(rng.choice([0.3, 0.2, 0.5])),
+        nscales=int(rng.integers(1, 8)),
+        warps=int(rng.integers(1, 7)),
+        epsilon=float(rng.choice([0.01, 0.02, 0.005, 0.05])),
+        scale_step=float(rng.choice([0.8, 0.7, 0.9, 0.6])),
+        inner_iterations=int(rng.choice([30, 7, 12, 2, 1, 33])),
+        outer_iterations=int(rng.choice([10, 3, 1, 5])),
+        median_filtering=int(rng.choice([5, 5, 1])),
+    )
+    pair = dict(seed=int(rng.integers(1, 10_000)), dx=float(rng.uniform(-3, 3)), dy=float(rng.uniform(-3, 3)),
+                shear=float(rng.uniform(-0.01, 0.01)), sigma=float(rng.choice([1.5, 2.0, 3.0])))
+    bands = bool(rng.integers(0, 3) == 0)
+    return h, w, kw, pair, bands
+
+
+@pytest.mark.parametrize("case", range(24))
+def test_random_config(gpu, orc, case):
+    rng = np.random.default_rng(1000 + case)
+    h, w, kw, pair, bands = draw(rng)
+    I0, I1 = synth.make_pair(h, w, **pair)
+    if bands:
+        I0 = I0.copy(); I1 = I1.copy()
+        I0[: h // 4] = 0; I1[: h // 4 + 2] = 0
+        I0[:, -(w // 5):] = 0; I1[:, -(w // 5):] = 0
+    okw = {("lambda" if k == "lambda_" else k): v for k, v in kw.items()}
+    ou, ov, oit, olev = orc.tvl1_calc(I0, I1, **okw)
+    for fused_min in (0, 1e18):
+        s = gpu.Solver(gpu.default_params(**kw))
+        s.set_option("fused_min_px", fused_min)
+        u, v = s.calc(I0, I1)
+        assert s.stats.levels == olev, (case, kw)
+        assert np.array_equal(s.stats.iters_array(), oit[:olev]), (case, kw, h, w)
+        assert np.array_equal(u, ou) and np.array_equal(v, ov), (case, kw, h, w, fused_min)
+        s.close()
