@@ -126,9 +126,20 @@ int launch_gradient(const float* src, int w, int h, int pitch, float* dx, float*
 
 int launch_warp(const WarpArgs& a, cudaStream_t st)
 {
+    // persistent blocks: one grid of resident blocks walks the tile list
+    static int cached[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int& resident = cached[dev & 63];
+    if (!resident) {
+        int sms = 148, occ = 0;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_warp, TVL1_WP_THREADS, 0) != cudaSuccess || occ < 1) occ = 2;
+        resident = sms * occ;
+    }
+    const long long ntiles = (long long)cdiv(a.w, TVL1_WP_TW) * cdiv(a.h, TVL1_WP_TH);
     dim3 b(32, TVL1_WP_NW);
-    dim3 g(cdiv(a.w, TVL1_WP_TW), cdiv(a.h, TVL1_WP_TH));
-    k_warp<<<g, b, 0, st>>>(a);
+    k_warp<<<(unsigned)(ntiles < resident ? ntiles : resident), b, 0, st>>>(a);
     CK(cudaGetLastError());
     return TVL1_OK;
 }
