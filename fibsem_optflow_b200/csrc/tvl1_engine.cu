@@ -232,9 +232,20 @@ int launch_iterate2(IterArgs& a, cudaStream_t st)
 
 int launch_median(const MedianArgs& a, int planes, cudaStream_t st)
 {
+    // persistent blocks: one grid of resident blocks walks the tile list of both planes
+    static int cached[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int& resident = cached[dev & 63];
+    if (!resident) {
+        int sms = 148, occ = 0;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_median5, 256, 0) != cudaSuccess || occ < 1) occ = 2;
+        resident = sms * occ;
+    }
+    const long long ntiles = (long long)cdiv(a.w, TVL1_MED_TW) * cdiv(a.h, TVL1_MED_TH) * planes;
     dim3 b(32, 8);
-    dim3 g(cdiv(a.w, TVL1_MED_TW), cdiv(a.h, TVL1_MED_TH), planes);
-    k_median5<<<g, b, 0, st>>>(a);
+    k_median5<<<(unsigned)(ntiles < resident ? ntiles : resident), b, 0, st>>>(a, planes);
     CK(cudaGetLastError());
     return TVL1_OK;
 }
