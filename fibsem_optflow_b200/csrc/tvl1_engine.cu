@@ -182,7 +182,7 @@ size_t iterate_max_blocks(int, int) { return 148 * 32 * 2; }
 // Rows per tile and grid size.  A tile is one warp's strip x R rows and every resident warp walks
 // the tile list with a grid stride: tall tiles amortise the halo rows (R / (R + halo)), but the
 // tile count has to spread evenly over the resident warps (no nearly empty last round).
-static int tile_rows(int w, int h, int strip, int halo, int rmin, int resident_blocks, int* grid)
+static int tile_rows_search(int w, int h, int strip, int halo, int rmin, int resident_blocks, int* grid)
 {
     const long long ns = cdiv(w, strip);
     const long long slots = (long long)resident_blocks * ITER_NW;
@@ -197,15 +197,36 @@ static int tile_rows(int w, int h, int strip, int halo, int rmin, int resident_b
         if (G < slots) eff *= (double)G / (double)slots;       // not even one tile per warp
         if (eff >= best) { best = eff; best_r = R; best_g = G; }
     }
-    if (const char* e = getenv(halo == 1 ? "TVL1_DEV_ROWS" : "TVL1_DEV_ROWS2")) {   // developer sweeps only
+    static const char* dev_rows[2] = {getenv("TVL1_DEV_ROWS"), getenv("TVL1_DEV_ROWS2")};   // developer sweeps only
+    if (const char* e = dev_rows[halo == 1 ? 0 : 1]) {
         best_r = atoi(e);
         const long long ntiles = ns * cdiv(h, best_r);
         best_g = ntiles < slots ? ntiles : slots;
     }
-    if (getenv("TVL1_DEV_VERBOSE"))
+    static const bool verbose = getenv("TVL1_DEV_VERBOSE") != nullptr;
+    if (verbose)
         fprintf(stderr, "tile_rows %dx%d strip %d: R=%d warps=%lld tiles=%lld\n", w, h, strip, best_r, best_g, ns * cdiv(h, best_r));
     *grid = (int)((best_g + ITER_NW - 1) / ITER_NW);
     return best_r;
+}
+
+// the search runs once per (size, kernel): a solve launches the same few shapes hundreds of times
+static int tile_rows(int w, int h, int strip, int halo, int rmin, int resident_blocks, int* grid)
+{
+    struct Entry { int w, h, strip, resident, rows, grid; };
+    static thread_local Entry cache[32];
+    static thread_local int used = 0, next = 0;
+    for (int i = 0; i < used; i++) {
+        const Entry& e = cache[i];
+        if (e.w == w && e.h == h && e.strip == strip && e.resident == resident_blocks) { *grid = e.grid; return e.rows; }
+    }
+    Entry e = {w, h, strip, resident_blocks, 0, 0};
+    e.rows = tile_rows_search(w, h, strip, halo, rmin, resident_blocks, &e.grid);
+    cache[next] = e;
+    next = (next + 1) % 32;
+    if (used < 32) used++;
+    *grid = e.grid;
+    return e.rows;
 }
 
 int launch_iterate(IterArgs& a, cudaStream_t st)

@@ -16,7 +16,7 @@ T, N = sys.argv[1], int(sys.argv[2])
 lines = [l for l in open("gpurun_out/launches_%s.csv" % T) if not l.startswith("==")]
 rows = [(r["Kernel Name"], float(r["Metric Value"].replace(",", ""))) for r in csv.DictReader(lines)
         if r.get("Metric Name") == "gpu__time_duration.sum"]
-for pat in ("k_iterate2", "k_iterate<", "k_median5", "k_warp"):
+for pat in ("k_iterate2", "k_median5", "k_warp"):
     idx = [i for i, (k, _) in enumerate(rows) if pat in k]
     if not idx:
         continue
