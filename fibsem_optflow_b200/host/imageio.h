@@ -41,9 +41,12 @@ inline uint32_t be32(const uint8_t* p) { return ((uint32_t)p[0] << 24) | ((uint3
 
 inline uint8_t rgb_to_gray(int r, int g, int b)
 {
-    // libpng png_set_rgb_to_gray(0.299, 0.587), the conversion OpenCV's PNG reader asks for:
-    // 15-bit fixed point, coefficients 9798 / 19235 / 3735
-    return (uint8_t)((9798 * r + 19235 * g + 3735 * b + 16384) >> 15);
+    // libpng png_set_rgb_to_gray(0.299, 0.587), the conversion OpenCV's PNG reader asks for when
+    // cv::imread is given IMREAD_GRAYSCALE: 15-bit fixed point with the coefficients libpng derives
+    // (29900 * 32768 / 100000 = 9797, 58700 * 32768 / 100000 = 19234, blue = the rest) and -- the
+    // historical libpng 1.6 path without a gamma table -- truncation.  Pinned against cv2.imread
+    // (tests/test_host_tools.py).
+    return (uint8_t)((9797 * r + 19234 * g + 3737 * b) >> 15);
 }
 
 inline bool decode_png(const std::vector<uint8_t>& f, Gray8& img, std::string& err)

@@ -1,0 +1,101 @@
+"""Host-side pieces of the job driver (N1), checked without a GPU through host/hosttool: the
+comment-tolerant JSON reader (the reference reads its job files with jsoncpp in non-strict mode,
+src/optflow.cpp:32-58, and docs/example.json relies on comments), jsoncpp's alphabetical member order
+(which fixes the order the reference walks "rois" in, :339), the PNG / PGM / TIFF readers that stand in
+for cv::imread(IMREAD_GRAYSCALE) (:106,:119) and the float TIFF writer (:480-481)."""
+import gzip
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST = os.path.join(ROOT, "fibsem_optflow_b200", "host")
+TOOL = os.path.join(HOST, "hosttool")
+
+
+@pytest.fixture(scope="module")
+def tool():
+    subprocess.check_call(["make", "-C", HOST, "-s", "hosttool"])
+    return TOOL
+
+
+def test_json_comments_order_numbers(tool, tmp_path):
+    text = """// job file in the style of docs/example.json
+    {
+      "style": 1, /* block comment */ "debug": false,
+      "rois": {"top": 100, "bottom": 120, "custom": [1, 2, 3, 4]},   // alphabetical walk: bottom, custom, top
+      "scale": 0.5, "lambda": 0.15, "big": 12345678901, "neg": -3, "exp": 1e-3,
+      "images": [ {"p": "a.png", "q": "b.png", "output_name": "a~b", }, ],
+      "s": "quote \\" and \\\\ and \\u00e9"
+    }"""
+    p = tmp_path / "job.json"
+    p.write_text(text)
+    out = subprocess.check_output([tool, "json", str(p)]).decode()
+    got = json.loads(out)
+    assert got["rois"] == {"bottom": 120, "custom": [1, 2, 3, 4], "top": 100}
+    assert list(got["rois"]) == ["bottom", "custom", "top"]          # jsoncpp member order
+    assert list(got)[:3] == sorted(got)[:3]
+    assert got["big"] == 12345678901 and got["neg"] == -3 and got["exp"] == 1e-3 and got["scale"] == 0.5
+    assert got["images"][0]["output_name"] == "a~b"
+    assert got["s"] == 'quote " and \\ and é'
+    assert '"big" : 12345678901' in out.replace("  ", " ") or "12345678901" in out   # integers stay integers
+
+
+def test_json_rejects_garbage(tool, tmp_path):
+    for bad in ('{"images": [ {"p": "x" "q": "y"} ]}',      # missing comma, as in docs/example.json:72
+                '{"a": 1', '[1, 2', '{"a": tru}', ''):
+        p = tmp_path / "bad.json"
+        p.write_text(bad)
+        assert subprocess.call([tool, "json", str(p)], stderr=subprocess.DEVNULL) != 0, bad
+
+
+def decode(tool, path):
+    raw = subprocess.check_output([tool, "image", str(path)])
+    head, _, body = raw.partition(b"\n")
+    w, h = (int(x) for x in head.split())
+    return np.frombuffer(body, np.uint8).reshape(h, w)
+
+
+@pytest.mark.parametrize("shape", [(37, 53), (128, 200), (1, 1), (5, 1000)])
+def test_image_readers_match_cv2(tool, tmp_path, shape):
+    cv2 = pytest.importorskip("cv2")
+    from PIL import Image
+    rng = np.random.default_rng(shape[0] * 1000 + shape[1])
+    a = rng.integers(0, 256, size=shape, dtype=np.uint8)
+    # 8-bit grey PNG (all five row filters occur on noise), PGM, uncompressed TIFF
+    assert cv2.imwrite(str(tmp_path / "g.png"), a, [cv2.IMWRITE_PNG_COMPRESSION, 6])
+    with open(tmp_path / "g.pgm", "wb") as f:
+        f.write(b"P5\n# c\n%d %d\n255\n" % (shape[1], shape[0]) + a.tobytes())
+    Image.fromarray(a).save(str(tmp_path / "g.tiff"), compression=None)
+    for name in ("g.png", "g.pgm", "g.tiff"):
+        assert np.array_equal(decode(tool, tmp_path / name), a), name
+    # colour and 16-bit PNGs go through the same conversion cv::imread(IMREAD_GRAYSCALE) applies
+    rgb = rng.integers(0, 256, size=shape + (3,), dtype=np.uint8)
+    assert cv2.imwrite(str(tmp_path / "c.png"), rgb)
+    want = cv2.imread(str(tmp_path / "c.png"), cv2.IMREAD_GRAYSCALE)
+    assert np.array_equal(decode(tool, tmp_path / "c.png"), want)
+    g16 = rng.integers(0, 65536, size=shape, dtype=np.uint16)
+    assert cv2.imwrite(str(tmp_path / "h.png"), g16)
+    want = cv2.imread(str(tmp_path / "h.png"), cv2.IMREAD_GRAYSCALE)
+    assert np.array_equal(decode(tool, tmp_path / "h.png"), want)
+
+
+def test_image_reader_errors(tool, tmp_path):
+    (tmp_path / "x.png").write_bytes(b"\x89PNG\r\n\x1a\n" + b"\0" * 10)
+    assert subprocess.call([tool, "image", str(tmp_path / "x.png")], stderr=subprocess.DEVNULL) != 0
+    assert subprocess.call([tool, "image", str(tmp_path / "missing.png")], stderr=subprocess.DEVNULL) != 0
+
+
+def test_float_tiff_writer_roundtrip(tool, tmp_path):
+    from PIL import Image
+    rng = np.random.default_rng(4)
+    a = rng.standard_normal((31, 45)).astype(np.float32)
+    a[0, 0] = -0.0
+    a[1, 1] = np.float32(1e-42)     # subnormal survives
+    out = tmp_path / "f.tiff"
+    subprocess.run([tool, "tiff", "45", "31", str(out)], input=a.tobytes(), check=True)
+    b = np.array(Image.open(str(out)))
+    assert b.dtype == np.float32 and np.array_equal(a.view(np.uint32), b.view(np.uint32))
