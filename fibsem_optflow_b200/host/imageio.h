@@ -1,10 +1,12 @@
 // imageio.h -- the image I/O the job driver needs, without OpenCV / libpng / libtiff.
 //
-// Stands in for cv::imread(..., IMREAD_GRAYSCALE) (reference src/optflow.cpp:106,119), the
-// optional prescale cv::resize(frame, Size(), scale, scale) (:113,125) and the float
-// cv::imwrite of the flow planes (:478-484).  Readers: PNG (8/16-bit grey, grey+alpha, RGB(A),
-// palette; non-interlaced) through zlib, binary PGM (P5) and uncompressed 8-bit grey baseline
-// TIFF.  Writer: uncompressed 32-bit float single-strip TIFF, which is what
+// Stands in for cv::imread(..., IMREAD_GRAYSCALE) (reference src/optflow.cpp:106,119) and the float
+// cv::imwrite of the flow planes (:478-484); the prescale cv::resize of :111,124 runs on the device
+// (tvl1_prescale_u8).  Readers: PNG (8/16-bit grey, grey+alpha, RGB(A), palette; non-interlaced)
+// through zlib, binary PGM (P5), and 8/16-bit grey TIFF in strips -- raw, PackBits, LZW or Deflate,
+// with or without the horizontal predictor (cv::imwrite's own TIFFs are LZW + predictor).  Colour is
+// reduced to grey and 16 bits to 8 the way cv::imread does it; every path is pinned against cv2
+// (tests/test_host_tools.py).  Writer: uncompressed 32-bit float single-strip TIFF, which is what
 // support_scripts/upload_matches.py opens with PIL (upload_matches.py:34-37).
 #pragma once
 #include <zlib.h>
@@ -173,7 +175,68 @@ inline bool decode_pgm(const std::vector<uint8_t>& f, Gray8& img, std::string& e
     return true;
 }
 
-// ---- TIFF (baseline, uncompressed) -----------------------------------------------------------
+// ---- TIFF: 8- or 16-bit grey in strips; uncompressed, PackBits, LZW or Deflate; horizontal predictor.
+// (cv::imwrite's own TIFFs are LZW + predictor 2.)  16-bit samples keep their high byte, which is what
+// cv::imread(IMREAD_GRAYSCALE) returns for them.
+
+// TIFF-flavoured LZW: MSB-first codes of 9..12 bits, ClearCode 256, EOI 257, "early change"
+inline bool tiff_lzw(const uint8_t* in, size_t n, std::vector<uint8_t>& out, size_t want)
+{
+    struct Entry { int prev; uint8_t first, last; uint16_t len; };
+    std::vector<Entry> tab(4096);
+    for (int i = 0; i < 256; i++) tab[i] = {-1, (uint8_t)i, (uint8_t)i, 1};
+    int next = 258, width = 9, prev = -1;
+    uint32_t acc = 0;
+    int bits = 0;
+    size_t pos = 0;
+    std::vector<uint8_t> tmp;
+    auto emit = [&](int code) {
+        const size_t len = tab[code].len, base = out.size();
+        out.resize(base + len);
+        for (size_t k = len; k-- > 0;) { out[base + k] = tab[code].last; code = tab[code].prev; }
+    };
+    while (out.size() < want) {
+        while (bits < width && pos < n) { acc = (acc << 8) | in[pos++]; bits += 8; }
+        if (bits < width) break;
+        const int code = (int)((acc >> (bits - width)) & ((1u << width) - 1));
+        bits -= width;
+        if (code == 257) break;
+        if (code == 256) { next = 258; width = 9; prev = -1; continue; }
+        if (prev < 0) {
+            if (code >= 256) return false;
+            emit(code);
+        } else if (code < next) {
+            emit(code);
+            if (next < 4096) { tab[next] = {prev, tab[prev].first, tab[code].first, (uint16_t)(tab[prev].len + 1)}; next++; }
+        } else if (code == next && next < 4096) {
+            tab[next] = {prev, tab[prev].first, tab[prev].first, (uint16_t)(tab[prev].len + 1)};
+            next++;
+            emit(code);
+        } else {
+            return false;
+        }
+        prev = code;
+        if (next + 1 >= (1 << width) && width < 12) width++;   // early change
+    }
+    return out.size() >= want;
+}
+
+inline bool tiff_packbits(const uint8_t* in, size_t n, std::vector<uint8_t>& out, size_t want)
+{
+    size_t p = 0;
+    while (p < n && out.size() < want) {
+        const int c = (int8_t)in[p++];
+        if (c >= 0) {
+            if (p + (size_t)c + 1 > n) return false;
+            out.insert(out.end(), in + p, in + p + c + 1);
+            p += (size_t)c + 1;
+        } else if (c != -128) {
+            if (p >= n) return false;
+            out.insert(out.end(), (size_t)(1 - c), in[p++]);
+        }
+    }
+    return out.size() >= want;
+}
 
 inline bool decode_tiff(const std::vector<uint8_t>& f, Gray8& img, std::string& err)
 {
@@ -188,7 +251,7 @@ inline bool decode_tiff(const std::vector<uint8_t>& f, Gray8& img, std::string& 
     size_t ifd = u32(4);
     if (ifd + 2 > f.size()) { err = "bad TIFF IFD"; return false; }
     const uint32_t n = u16(ifd);
-    uint32_t w = 0, h = 0, bits = 1, spp = 1, comp = 1, photo = 1, rps = 0xffffffffu;
+    uint32_t w = 0, h = 0, bits = 1, spp = 1, comp = 1, photo = 1, rps = 0xffffffffu, pred = 1, tiled = 0;
     std::vector<uint32_t> offs, counts;
     for (uint32_t k = 0; k < n; k++) {
         const size_t e = ifd + 2 + 12 * (size_t)k;
@@ -196,6 +259,7 @@ inline bool decode_tiff(const std::vector<uint8_t>& f, Gray8& img, std::string& 
         const uint32_t tag = u16(e), type = u16(e + 2), cnt = u32(e + 4);
         const size_t esz = type == 3 ? 2 : (type == 4 ? 4 : 1);
         const size_t vo = cnt * esz <= 4 ? e + 8 : u32(e + 8);
+        if (vo + cnt * esz > f.size()) { err = "bad TIFF IFD"; return false; }
         auto val = [&](uint32_t i) -> uint32_t { return type == 3 ? u16(vo + 2 * i) : (type == 4 ? u32(vo + 4 * i) : f[vo + i]); };
         switch (tag) {
             case 256: w = val(0); break;
@@ -205,25 +269,63 @@ inline bool decode_tiff(const std::vector<uint8_t>& f, Gray8& img, std::string& 
             case 262: photo = val(0); break;
             case 277: spp = val(0); break;
             case 278: rps = val(0); break;
+            case 317: pred = val(0); break;
+            case 322: tiled = 1; break;
             case 273: for (uint32_t i = 0; i < cnt; i++) offs.push_back(val(i)); break;
             case 279: for (uint32_t i = 0; i < cnt; i++) counts.push_back(val(i)); break;
             default: break;
         }
     }
-    if (!w || !h || bits != 8 || spp != 1 || comp != 1 || offs.empty()) {
-        err = "only uncompressed 8-bit single-channel TIFF is supported";
+    const bool comp_ok = comp == 1 || comp == 5 || comp == 8 || comp == 32946 || comp == 32773;
+    if (!w || !h || (bits != 8 && bits != 16) || spp != 1 || !comp_ok || pred > 2 || tiled || photo > 1 || offs.empty() ||
+        counts.size() != offs.size()) {
+        err = "only 8/16-bit single-channel TIFF in strips (raw, PackBits, LZW, Deflate) is supported";
         return false;
     }
     if (rps > h) rps = h;
+    const size_t bps = bits / 8, rowbytes = (size_t)w * bps;
     img.w = (int)w; img.h = (int)h;
     img.px.resize((size_t)w * h);
     size_t row = 0;
+    std::vector<uint8_t> buf;
     for (size_t s = 0; s < offs.size() && row < h; s++) {
-        const size_t rows = std::min<size_t>(rps, h - row), bytes = rows * w;
-        if (offs[s] + bytes > f.size()) { err = "truncated TIFF strip"; return false; }
-        std::memcpy(&img.px[row * w], &f[offs[s]], bytes);
+        const size_t rows = std::min<size_t>(rps, h - row), bytes = rows * rowbytes;
+        if ((size_t)offs[s] + counts[s] > f.size()) { err = "truncated TIFF strip"; return false; }
+        const uint8_t* src = &f[offs[s]];
+        buf.clear();
+        bool ok = true;
+        if (comp == 1) {
+            if (counts[s] < bytes) ok = false; else buf.assign(src, src + bytes);
+        } else if (comp == 5) {
+            buf.reserve(bytes);
+            ok = tiff_lzw(src, counts[s], buf, bytes);
+        } else if (comp == 32773) {
+            buf.reserve(bytes);
+            ok = tiff_packbits(src, counts[s], buf, bytes);
+        } else {
+            buf.resize(bytes);
+            uLongf got = (uLongf)bytes;
+            ok = uncompress(buf.data(), &got, src, (uLong)counts[s]) == Z_OK && got >= bytes;
+        }
+        if (!ok) { err = "corrupt TIFF strip"; return false; }
+        for (size_t r = 0; r < rows; r++) {
+            uint8_t* line = &buf[r * rowbytes];
+            uint8_t* o = &img.px[(row + r) * w];
+            if (bits == 8) {
+                if (pred == 2) for (size_t x = 1; x < w; x++) line[x] = (uint8_t)(line[x] + line[x - 1]);
+                std::memcpy(o, line, w);
+            } else {
+                uint16_t acc = 0;
+                for (size_t x = 0; x < w; x++) {
+                    uint16_t v = le ? (uint16_t)(line[2 * x] | (line[2 * x + 1] << 8)) : (uint16_t)((line[2 * x] << 8) | line[2 * x + 1]);
+                    if (pred == 2) { acc = (uint16_t)(acc + v); v = acc; }
+                    o[x] = (uint8_t)(v >> 8);
+                }
+            }
+        }
         row += rows;
     }
+    if (row < h) { err = "TIFF strips do not cover the image"; return false; }
     if (photo == 0) for (auto& v : img.px) v = (uint8_t)(255 - v);   // WhiteIsZero
     return true;
 }

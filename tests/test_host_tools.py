@@ -72,6 +72,19 @@ def test_image_readers_match_cv2(tool, tmp_path, shape):
     Image.fromarray(a).save(str(tmp_path / "g.tiff"), compression=None)
     for name in ("g.png", "g.pgm", "g.tiff"):
         assert np.array_equal(decode(tool, tmp_path / name), a), name
+    # compressed TIFFs: cv::imwrite's own (LZW + horizontal predictor), PackBits, Deflate, LZW without predictor
+    assert cv2.imwrite(str(tmp_path / "cv.tiff"), a)
+    assert np.array_equal(decode(tool, tmp_path / "cv.tiff"), a)
+    smooth = (np.add.outer(np.arange(shape[0]), np.arange(shape[1])) // 3 % 256).astype(np.uint8)   # long LZW strings
+    assert cv2.imwrite(str(tmp_path / "cvs.tiff"), smooth)
+    assert np.array_equal(decode(tool, tmp_path / "cvs.tiff"), smooth)
+    for comp in ("packbits", "tiff_adobe_deflate", "tiff_lzw"):
+        for arr in (a, smooth):
+            Image.fromarray(arr).save(str(tmp_path / "p.tiff"), compression=comp)
+            assert np.array_equal(decode(tool, tmp_path / "p.tiff"), arr), comp
+    g16t = rng.integers(0, 65536, size=shape, dtype=np.uint16)
+    assert cv2.imwrite(str(tmp_path / "h.tiff"), g16t)
+    assert np.array_equal(decode(tool, tmp_path / "h.tiff"), cv2.imread(str(tmp_path / "h.tiff"), cv2.IMREAD_GRAYSCALE))
     # colour and 16-bit PNGs go through the same conversion cv::imread(IMREAD_GRAYSCALE) applies
     rgb = rng.integers(0, 256, size=shape + (3,), dtype=np.uint8)
     assert cv2.imwrite(str(tmp_path / "c.png"), rgb)
