@@ -151,12 +151,12 @@ static const int ITER_NW = TVL1_ITER_NW;
 
 // resident blocks of the iteration kernels on the current device (SMs x occupancy), queried once
 // per device; the fused kernel's shared-memory ring needs the opt-in limit raised first
-enum { KI_SMALL = 0, KI_LARGE = 1, KI_FUSED = 2 };   // k_iterate<.,5>, k_iterate<.,4>, k_iterate2
+enum { KI_SMALL = 0, KI_LARGE = 1, KI_FUSED = 2, KI_MULTI = 3 };   // k_iterate<.,5>, k_iterate<.,4>, k_iterate2, k_iterate_multi
 static const long long ITER_LARGE_PX = 16000000;     // levels at least this large: 4 blocks per SM
 
 static int resident_blocks(int which)
 {
-    static int cached[3][64] = {};
+    static int cached[4][64] = {};
     int dev = 0, sms = 148, occ = 0;
     cudaGetDevice(&dev);
     int& c = cached[which][dev & 63];
@@ -167,6 +167,8 @@ static int resident_blocks(int which)
         // the shared-memory ring needs the opt-in limit raised first
         cudaFuncSetAttribute(k_iterate2<ITER_NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, TVL1_RING_BYTES(ITER_NW));
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_iterate2<ITER_NW>, 32 * ITER_NW, TVL1_RING_BYTES(ITER_NW));
+    } else if (which == KI_MULTI) {
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_iterate_multi<ITER_NW, 4>, 32 * ITER_NW, 0);
     } else if (which == KI_LARGE) {
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_iterate<ITER_NW, 4>, 32 * ITER_NW, 0);
     } else {
@@ -241,6 +243,29 @@ int launch_iterate(IterArgs& a, cudaStream_t st)
     return TVL1_OK;
 }
 
+// several iterations in one cooperative launch (small levels); the grid must be co-resident
+int launch_iterate_multi(IterArgs& a, cudaStream_t st)
+{
+    // these levels are bound by latency, not by throughput: the shortest tiles that still give every
+    // tile its own warp (one round) make an iteration a chain of R + 1 dependent row steps only
+    const int resident = resident_blocks(KI_MULTI);
+    const long long slots = (long long)resident * ITER_NW, ns = cdiv(a.w, TVL1_STRIP);
+    int grid = 1, R = 0;
+    for (int r = 1; r <= 8 && !R; ++r)
+        if (ns * cdiv(a.h, r) <= slots) R = r;
+    if (R) {
+        a.rows = R;
+        grid = (int)((ns * cdiv(a.h, R) + ITER_NW - 1) / ITER_NW);
+    } else {
+        a.rows = tile_rows(a.w, a.h, TVL1_STRIP, 1, 4, resident, &grid);
+    }
+    dim3 b(32, ITER_NW), g(grid);
+    void* args[] = {(void*)&a};
+    cudaError_t e = cudaLaunchCooperativeKernel((const void*)k_iterate_multi<ITER_NW, 4>, g, b, args, 0, st);
+    if (e != cudaSuccess) return fail(TVL1_ERR_CUDA, "cooperative launch of k_iterate_multi failed: %s", cudaGetErrorString(e));
+    return TVL1_OK;
+}
+
 int launch_iterate2(IterArgs& a, cudaStream_t st)
 {
     int grid = 1;
@@ -287,6 +312,7 @@ struct tvl1_handle {
     tvl1_params prm;
     int inner = 30, outer = 10;
     bool timing = false;
+    bool multi_iter = true;             // levels below fused_min_px: all inner iterations of an outer one in ONE cooperative launch
     long long fused_min_px = 1500000;   // levels at least this large use the two-iteration kernel (measured cross-over ~1.2 Mpx)
     // arena
     char* arena = nullptr;
@@ -504,6 +530,7 @@ static int calc_device(tvl1_handle* H, const uint8_t* f0, size_t pitch0, const u
         ia.level = s; ia.ctrl = H->d_ctrl; ia.partials = H->d_partials; ia.errlog = nullptr;
         ia.mode = 0; ia.inner_max = H->inner;
         const bool fused = (long long)lv.w * lv.h >= H->fused_min_px && H->inner >= 2;
+        const bool multi = !fused && H->multi_iter && H->inner >= 2;
         MedianArgs ma;
         ma.u1[0] = lv.u1; ma.u1[1] = H->u1x; ma.u2[0] = lv.u2; ma.u2[1] = H->u2x;
         ma.w = lv.w; ma.h = lv.h; ma.pitch = lv.pitch; ma.level = s; ma.ctrl = H->d_ctrl;
@@ -559,6 +586,12 @@ static int calc_device(tvl1_handle* H, const uint8_t* f0, size_t pitch0, const u
                             if ((rc = launch_iterate(i1, st))) return rc;
                         }
                         launches += 2 * groups;
+                    } else if (multi) {
+                        // small level: one cooperative launch runs the rest of this outer iteration
+                        IterArgs im = ia;
+                        im.mode = 3;
+                        if ((rc = launch_iterate_multi(im, st))) return rc;
+                        launches += 1;
                     } else {
                         IterArgs i3 = ia;
                         i3.mode = 3;
@@ -733,6 +766,7 @@ int tvl1_set_option(tvl1_handle* H, const char* key, double value)
 {
     if (!H || !key) return fail(TVL1_ERR_INVALID, "null handle or key");
     if (!strcmp(key, "fused_min_px")) { H->fused_min_px = value < 0 ? 0 : (long long)value; return TVL1_OK; }
+    if (!strcmp(key, "multi_iter")) { H->multi_iter = value != 0; return TVL1_OK; }
     return fail(TVL1_ERR_INVALID, "unknown option '%s'", key);
 }
 
