@@ -50,6 +50,7 @@ struct DeviceFrame {
 
 struct Driver {
     int device = 0;
+    int prefetch = 4;       // pairs whose frames are decoded ahead on host threads
     tvl1_handle* solver = nullptr;
     tvl1_params cur{};
     bool have_params = false;
@@ -359,14 +360,19 @@ int from_file(Driver& D, Value& args, int shard, int nshards)
             return finish_frame(D.device, name, std::move(d), scale, out);
         };
         const bool have = fetch(n0, frame0) && fetch(n1, frame1);
-        // decode what the next pair will need while this one is solved (a slice shared with this
-        // pair comes out of the cache instead)
-        if (i + 1 < end) {
-            const Value& nx = images[i + 1];
-            if (nx.isMember("p") && nx.isMember("q")) {
+        // decode what the next pairs will need on host threads while this one is solved (decoding an
+        // 8k x 8k PNG takes far longer than its solve, so the look-ahead -- not the GPU -- sets the pace
+        // of a job); a frame this pair or an earlier look-ahead already covers is not decoded twice
+        {
+            std::string prev0 = n0, prev1 = n1;
+            for (size_t j = i + 1; j < end && j <= i + (size_t)D.prefetch; j++) {
+                const Value& nx = images[j];
+                if (!nx.isMember("p") || !nx.isMember("q")) break;
                 const std::string m0 = nx.at("p").asString(), m1 = nx.at("q").asString();
-                if (m0 != n0 && m0 != n1) prefetch(m0);
-                if (m1 != n0 && m1 != n1 && m1 != m0) prefetch(m1);
+                // the two-slot frame cache will still hold the previous pair's frames when pair j is reached
+                if (m0 != prev0 && m0 != prev1) prefetch(m0);
+                if (m1 != prev0 && m1 != prev1 && m1 != m0) prefetch(m1);
+                prev0 = m0; prev1 = m1;
             }
         }
         if (!have) continue;
@@ -407,15 +413,19 @@ int from_file(Driver& D, Value& args, int shard, int nshards)
 int main(int argc, const char* argv[])
 {
     std::string filename;
-    int device = 0, shard = 0, nshards = 1;
+    int device = 0, shard = 0, nshards = 1, prefetch = 4;
     for (int k = 1; k < argc; k++) {
         const std::string a = argv[k];
         if (a == "-h" || a == "--help") {
-            std::cout << "usage: optflow_b200 [--device N] [--shard RANK/WORLD] <job.json[.gz]>\n"
-                         "  --shard: solve only this rank's contiguous block of \"images\" (one process per GPU)\n";
+            std::cout << "usage: optflow_b200 [--device N] [--shard RANK/WORLD] [--prefetch N] <job.json[.gz]>\n"
+                         "  --shard: solve only this rank's contiguous block of \"images\" (one process per GPU)\n"
+                         "  --prefetch: pairs whose frames are decoded ahead on host threads (default 4)\n";
             return 0;
         } else if (a == "--device" && k + 1 < argc) {
             device = std::atoi(argv[++k]);
+        } else if (a == "--prefetch" && k + 1 < argc) {
+            prefetch = std::atoi(argv[++k]);
+            if (prefetch < 0 || prefetch > 64) die("--prefetch wants 0..64");
         } else if (a == "--shard" && k + 1 < argc) {
             if (std::sscanf(argv[++k], "%d/%d", &shard, &nshards) != 2 || nshards < 1 || shard < 0 || shard >= nshards)
                 die("--shard wants RANK/WORLD");
@@ -435,5 +445,6 @@ int main(int argc, const char* argv[])
     if (style != 1) die("only \"style\": 1 exists");
     Driver D;
     D.device = device;
+    D.prefetch = prefetch;
     return from_file(D, args, shard, nshards);
 }
