@@ -2,7 +2,7 @@
 //
 // Stands in for cv::imread(..., IMREAD_GRAYSCALE) (reference src/optflow.cpp:106,119) and the float
 // cv::imwrite of the flow planes (:478-484); the prescale cv::resize of :111,124 runs on the device
-// (tvl1_prescale_u8).  Readers: PNG (8/16-bit grey, grey+alpha, RGB(A), palette; non-interlaced)
+// (tvl1_prescale_u8).  Readers: PNG (8/16-bit grey, grey+alpha, RGB(A), palette; plain or Adam7-interlaced)
 // through zlib, binary PGM (P5), and 8/16-bit grey TIFF in strips -- raw, PackBits, LZW or Deflate,
 // with or without the horizontal predictor (cv::imwrite's own TIFFs are LZW + predictor).  Colour is
 // reduced to grey and 16 bits to 8 the way cv::imread does it; every path is pinned against cv2
@@ -75,7 +75,7 @@ inline bool decode_png(const std::vector<uint8_t>& f, Gray8& img, std::string& e
         p += 12 + len;
     }
     if (w <= 0 || h <= 0) { err = "PNG without IHDR"; return false; }
-    if (interlace) { err = "interlaced PNG is not supported"; return false; }
+    if (interlace > 1) { err = "bad PNG interlace method"; return false; }
     int channels;
     switch (ctype) {
         case 0: channels = 1; break;
@@ -87,65 +87,84 @@ inline bool decode_png(const std::vector<uint8_t>& f, Gray8& img, std::string& e
     }
     if (!(depth == 8 || depth == 16 || (depth < 8 && (ctype == 0 || ctype == 3)))) { err = "unsupported PNG bit depth"; return false; }
     const size_t bpp_bits = (size_t)channels * depth;
-    const size_t stride = ((size_t)w * bpp_bits + 7) / 8;
     const size_t bpp = bpp_bits >= 8 ? bpp_bits / 8 : 1;
-    std::vector<uint8_t> raw((stride + 1) * (size_t)h);
+    // the sub-images of the stream: the whole image, or the seven Adam7 passes
+    struct Pass { int x0, y0, dx, dy, pw, ph; size_t stride; };
+    std::vector<Pass> passes;
+    if (!interlace) {
+        passes.push_back({0, 0, 1, 1, w, h, ((size_t)w * bpp_bits + 7) / 8});
+    } else {
+        static const int X0[7] = {0, 4, 0, 2, 0, 1, 0}, Y0[7] = {0, 0, 4, 0, 2, 0, 1};
+        static const int DX[7] = {8, 8, 4, 4, 2, 2, 1}, DY[7] = {8, 8, 8, 4, 4, 2, 2};
+        for (int k = 0; k < 7; k++) {
+            const int pw = (w - X0[k] + DX[k] - 1) / DX[k], ph = (h - Y0[k] + DY[k] - 1) / DY[k];
+            if (pw > 0 && ph > 0) passes.push_back({X0[k], Y0[k], DX[k], DY[k], pw, ph, ((size_t)pw * bpp_bits + 7) / 8});
+        }
+    }
+    size_t total = 0;
+    for (const Pass& ps : passes) total += (ps.stride + 1) * (size_t)ps.ph;
+    std::vector<uint8_t> raw(total);
     uLongf rawlen = (uLongf)raw.size();
     if (uncompress(raw.data(), &rawlen, idat.data(), (uLong)idat.size()) != Z_OK || rawlen != raw.size()) {
         err = "PNG inflate failed";
         return false;
     }
-    // unfilter in place
-    std::vector<uint8_t> prev(stride, 0);
-    for (int y = 0; y < h; y++) {
-        uint8_t* row = &raw[(stride + 1) * (size_t)y];
-        const int ft = row[0];
-        uint8_t* c = row + 1;
-        for (size_t i = 0; i < stride; i++) {
-            const int a = i >= bpp ? c[i - bpp] : 0, b = prev[i], cc = i >= bpp ? prev[i - bpp] : 0;
-            int v = c[i];
-            switch (ft) {
-                case 0: break;
-                case 1: v += a; break;
-                case 2: v += b; break;
-                case 3: v += (a + b) >> 1; break;
-                case 4: {
-                    const int pa = std::abs(b - cc), pb = std::abs(a - cc), pc = std::abs(a + b - 2 * cc);
-                    v += (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : cc);
-                    break;
-                }
-                default: err = "bad PNG filter"; return false;
-            }
-            c[i] = (uint8_t)v;
-        }
-        std::memcpy(prev.data(), c, stride);
-    }
     img.w = w; img.h = h;
     img.px.resize((size_t)w * h);
-    for (int y = 0; y < h; y++) {
-        const uint8_t* c = &raw[(stride + 1) * (size_t)y + 1];
-        uint8_t* o = &img.px[(size_t)y * w];
-        for (int x = 0; x < w; x++) {
-            if (ctype == 0 || ctype == 4) {
-                if (depth == 8) o[x] = c[(size_t)x * channels];
-                else if (depth == 16) o[x] = c[(size_t)x * channels * 2];   // high byte, like libpng's strip_16
-                else {
-                    const int per = 8 / depth, sh = (per - 1 - x % per) * depth;
-                    const int v = (c[x / per] >> sh) & ((1 << depth) - 1);
-                    o[x] = (uint8_t)(v * 255 / ((1 << depth) - 1));
-                }
-            } else if (ctype == 3) {
-                int idx;
-                if (depth == 8) idx = c[x];
-                else { const int per = 8 / depth, sh = (per - 1 - x % per) * depth; idx = (c[x / per] >> sh) & ((1 << depth) - 1); }
-                if ((size_t)idx * 3 + 2 >= plte.size()) { err = "PNG palette index out of range"; return false; }
-                o[x] = rgb_to_gray(plte[idx * 3], plte[idx * 3 + 1], plte[idx * 3 + 2]);
-            } else {
-                const size_t step = depth == 16 ? 2 : 1;
-                const uint8_t* q = c + (size_t)x * channels * step;
-                o[x] = rgb_to_gray(q[0], q[step], q[2 * step]);
+    // one pixel of an unfiltered scanline -> 8-bit grey, the way cv::imread(IMREAD_GRAYSCALE) reduces it
+    auto to_gray = [&](const uint8_t* c, int x, uint8_t& out) -> bool {
+        if (ctype == 0 || ctype == 4) {
+            if (depth == 8) out = c[(size_t)x * channels];
+            else if (depth == 16) out = c[(size_t)x * channels * 2];   // high byte, like libpng's strip_16
+            else {
+                const int per = 8 / depth, sh = (per - 1 - x % per) * depth;
+                const int v = (c[x / per] >> sh) & ((1 << depth) - 1);
+                out = (uint8_t)(v * 255 / ((1 << depth) - 1));
             }
+        } else if (ctype == 3) {
+            int idx;
+            if (depth == 8) idx = c[x];
+            else { const int per = 8 / depth, sh = (per - 1 - x % per) * depth; idx = (c[x / per] >> sh) & ((1 << depth) - 1); }
+            if ((size_t)idx * 3 + 2 >= plte.size()) return false;
+            out = rgb_to_gray(plte[idx * 3], plte[idx * 3 + 1], plte[idx * 3 + 2]);
+        } else {
+            const size_t step = depth == 16 ? 2 : 1;
+            const uint8_t* q = c + (size_t)x * channels * step;
+            out = rgb_to_gray(q[0], q[step], q[2 * step]);
         }
+        return true;
+    };
+    size_t base = 0;
+    for (const Pass& ps : passes) {
+        const size_t stride = ps.stride;
+        std::vector<uint8_t> prev(stride, 0);
+        for (int y = 0; y < ps.ph; y++) {
+            uint8_t* row = &raw[base + (stride + 1) * (size_t)y];
+            const int ft = row[0];
+            uint8_t* c = row + 1;
+            for (size_t i = 0; i < stride; i++) {   // unfilter in place
+                const int a = i >= bpp ? c[i - bpp] : 0, b = prev[i], cc = i >= bpp ? prev[i - bpp] : 0;
+                int v = c[i];
+                switch (ft) {
+                    case 0: break;
+                    case 1: v += a; break;
+                    case 2: v += b; break;
+                    case 3: v += (a + b) >> 1; break;
+                    case 4: {
+                        const int pa = std::abs(b - cc), pb = std::abs(a - cc), pc = std::abs(a + b - 2 * cc);
+                        v += (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : cc);
+                        break;
+                    }
+                    default: err = "bad PNG filter"; return false;
+                }
+                c[i] = (uint8_t)v;
+            }
+            std::memcpy(prev.data(), c, stride);
+            uint8_t* o = &img.px[(size_t)(ps.y0 + y * ps.dy) * w + ps.x0];
+            for (int x = 0; x < ps.pw; x++)
+                if (!to_gray(c, x, o[(size_t)x * ps.dx])) { err = "PNG palette index out of range"; return false; }
+        }
+        base += (stride + 1) * (size_t)ps.ph;
     }
     return true;
 }

@@ -82,6 +82,35 @@ def test_image_readers_match_cv2(tool, tmp_path, shape):
         for arr in (a, smooth):
             Image.fromarray(arr).save(str(tmp_path / "p.tiff"), compression=comp)
             assert np.array_equal(decode(tool, tmp_path / "p.tiff"), arr), comp
+    # Adam7-interlaced PNGs (grey and colour) and a palette PNG, written by PIL
+    import zlib, struct
+
+    def png_bytes(arr, ctype, interlace):
+        """minimal PNG writer (filter 0) so that the Adam7 path is exercised independently of PIL"""
+        hh, ww = arr.shape[:2]
+        ch = 1 if arr.ndim == 2 else arr.shape[2]
+        def chunk(tag, data):
+            return struct.pack(">I", len(data)) + tag + data + struct.pack(">I", zlib.crc32(tag + data) & 0xffffffff)
+        if not interlace:
+            rows = b"".join(b"\0" + arr[y].tobytes() for y in range(hh))
+        else:
+            X0, Y0 = (0, 4, 0, 2, 0, 1, 0), (0, 0, 4, 0, 2, 0, 1)
+            DX, DY = (8, 8, 4, 4, 2, 2, 1), (8, 8, 8, 4, 4, 2, 2)
+            rows = b""
+            for k in range(7):
+                sub = arr[Y0[k]::DY[k], X0[k]::DX[k]]
+                if sub.shape[0] and sub.shape[1]:
+                    rows += b"".join(b"\0" + np.ascontiguousarray(sub[y]).tobytes() for y in range(sub.shape[0]))
+        ihdr = struct.pack(">IIBBBBB", ww, hh, 8, ctype, 0, 0, 1 if interlace else 0)
+        return b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", ihdr) + chunk(b"IDAT", zlib.compress(rows)) + chunk(b"IEND", b"")
+
+    rgb_i = rng.integers(0, 256, size=shape + (3,), dtype=np.uint8)
+    for (arr, ctype) in ((a, 0), (rgb_i, 2)):
+        (tmp_path / "i.png").write_bytes(png_bytes(arr, ctype, True))
+        want_i = cv2.imread(str(tmp_path / "i.png"), cv2.IMREAD_GRAYSCALE)
+        assert want_i is not None and np.array_equal(decode(tool, tmp_path / "i.png"), want_i), ctype
+    Image.fromarray(a).convert("P").save(str(tmp_path / "pal.png"))
+    assert np.array_equal(decode(tool, tmp_path / "pal.png"), cv2.imread(str(tmp_path / "pal.png"), cv2.IMREAD_GRAYSCALE))
     g16t = rng.integers(0, 65536, size=shape, dtype=np.uint16)
     assert cv2.imwrite(str(tmp_path / "h.tiff"), g16t)
     assert np.array_equal(decode(tool, tmp_path / "h.tiff"), cv2.imread(str(tmp_path / "h.tiff"), cv2.IMREAD_GRAYSCALE))
@@ -112,3 +141,24 @@ def test_float_tiff_writer_roundtrip(tool, tmp_path):
     subprocess.run([tool, "tiff", "45", "31", str(out)], input=a.tobytes(), check=True)
     b = np.array(Image.open(str(out)))
     assert b.dtype == np.float32 and np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+def test_driver_cli_without_gpu(tmp_path):
+    """The job driver itself: --help needs no device; argument errors and unreadable job files fail
+    loudly before any CUDA call; and without a device the driver refuses to run (there is no CPU path)."""
+    subprocess.check_call(["make", "-C", HOST, "-s", "optflow_b200"])
+    exe = os.path.join(HOST, "optflow_b200")
+    out = subprocess.check_output([exe, "--help"]).decode()
+    assert "--shard" in out and "--prefetch" in out
+    assert subprocess.call([exe], stderr=subprocess.DEVNULL, stdout=subprocess.DEVNULL) != 0            # no job file
+    assert subprocess.call([exe, "--shard", "3/2", "x.json"], stderr=subprocess.DEVNULL, stdout=subprocess.DEVNULL) != 0
+    bad = tmp_path / "bad.json"
+    bad.write_text('{"images": [ {"p": "x" "q": "y"} ]}')
+    assert subprocess.call([exe, str(bad)], stderr=subprocess.DEVNULL, stdout=subprocess.DEVNULL) != 0
+    import ctypes
+    lib = ctypes.CDLL(os.path.join(ROOT, "fibsem_optflow_b200", "csrc", "libtvl1_b200.so"))
+    if lib.tvl1_dev_count() <= 0:
+        good = tmp_path / "job.json"
+        good.write_text(json.dumps({"images": [], "output_dir": str(tmp_path)}))
+        p = subprocess.run([exe, str(good)], capture_output=True)
+        assert p.returncode != 0 and b"no CUDA device" in p.stderr + p.stdout

@@ -195,3 +195,24 @@ def test_prescale_golden(orc):
     for k in range(int(g["n"])):
         got = orc.prescale_u8(g["src_%d" % k], float(g["scale_%d" % k]))
         assert got.shape == g["dst_%d" % k].shape and np.array_equal(got, g["dst_%d" % k]), k
+
+
+@pytest.mark.parametrize("h,w,seed,kw", [
+    (90, 140, 3, dict(lambda_=0.05, nscales=10, warps=3)),                          # wrapper defaults: as many scales as fit
+    (77, 101, 5, dict(scale_step=0.7, theta=0.25, tau=0.2, epsilon=0.02, nscales=4)),
+    (64, 80, 9, dict(median_filtering=1, inner_iterations=11, outer_iterations=4, nscales=3)),
+    (130, 70, 2, dict(scale_step=0.9, nscales=6, warps=2, lambda_=0.3)),
+])
+def test_whole_pair_vs_cv2_composition_params(orc, cv2_plain, h, w, seed, kw):
+    """The C oracle against the composition made of the REAL cv2.resize / cv2.remap / cv2.medianBlur
+    (oracle/tvl1_ref.py) over the parameter space, zero band included: flow bit-equal, iteration counts equal."""
+    from fibsem_optflow_b200 import synth
+    from oracle import tvl1_ref
+    I0, I1 = synth.make_pair(h, w, seed=seed, dx=1.7, dy=0.6)
+    I0 = I0.copy(); I0[: h // 5] = 0
+    okw = {("lambda" if k == "lambda_" else k): v for k, v in kw.items()}
+    u, v, it, lev = orc.tvl1_calc(I0, I1, **okw)
+    ru, rv, rit = tvl1_ref.tvl1_calc(I0, I1, **kw)
+    assert lev == rit.shape[0]
+    assert np.array_equal(it[:lev], rit)
+    assert np.array_equal(u, ru) and np.array_equal(v, rv)
