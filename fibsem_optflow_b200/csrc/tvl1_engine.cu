@@ -151,12 +151,12 @@ static const int ITER_NW = TVL1_ITER_NW;
 
 // resident blocks of the iteration kernels on the current device (SMs x occupancy), queried once
 // per device; the fused kernel's shared-memory ring needs the opt-in limit raised first
-enum { KI_SMALL = 0, KI_LARGE = 1, KI_FUSED = 2, KI_MULTI = 3 };   // k_iterate<.,5>, k_iterate<.,4>, k_iterate2, k_iterate_multi
+enum { KI_SMALL = 0, KI_LARGE = 1, KI_FUSED = 2, KI_MULTI = 3, KI_OUTER = 4 };   // k_iterate<.,5>, k_iterate<.,4>, k_iterate2, k_iterate_multi
 static const long long ITER_LARGE_PX = 16000000;     // levels at least this large: 4 blocks per SM
 
 static int resident_blocks(int which)
 {
-    static int cached[4][64] = {};
+    static int cached[5][64] = {};
     int dev = 0, sms = 148, occ = 0;
     cudaGetDevice(&dev);
     int& c = cached[which][dev & 63];
@@ -167,6 +167,9 @@ static int resident_blocks(int which)
         // the shared-memory ring needs the opt-in limit raised first
         cudaFuncSetAttribute(k_iterate2<ITER_NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, TVL1_RING_BYTES(ITER_NW));
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_iterate2<ITER_NW>, 32 * ITER_NW, TVL1_RING_BYTES(ITER_NW));
+    } else if (which == KI_OUTER) {
+        cudaFuncSetAttribute(k_outer<ITER_NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, TVL1_RING_BYTES(ITER_NW));
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_outer<ITER_NW>, 32 * ITER_NW, TVL1_RING_BYTES(ITER_NW));
     } else if (which == KI_MULTI) {
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_iterate_multi<ITER_NW, 4>, 32 * ITER_NW, 0);
     } else if (which == KI_LARGE) {
@@ -174,7 +177,7 @@ static int resident_blocks(int which)
     } else {
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_iterate<ITER_NW, 5>, 32 * ITER_NW, 0);
     }
-    if (e != cudaSuccess || occ < 1) occ = which == KI_FUSED ? 3 : 4;
+    if (e != cudaSuccess || occ < 1) occ = (which == KI_FUSED || which == KI_OUTER) ? 3 : 4;
     c = sms * occ;
     return c;
 }
@@ -266,6 +269,20 @@ int launch_iterate_multi(IterArgs& a, cudaStream_t st)
     return TVL1_OK;
 }
 
+// the inner loop of one outer iteration (fused + single passes) in one cooperative launch
+int launch_outer(IterArgs& a, cudaStream_t st)
+{
+    int grid = 1, g1 = 1;
+    const int resident = resident_blocks(KI_OUTER);
+    a.rows = tile_rows(a.w, a.h, TVL1_STRIP2, 3, 8, resident, &grid);
+    a.rows1 = tile_rows(a.w, a.h, TVL1_STRIP, 1, 4, resident, &g1);   // its single passes stride over the same grid
+    dim3 b(32, ITER_NW), g(grid);
+    void* args[] = {(void*)&a};
+    cudaError_t e = cudaLaunchCooperativeKernel((const void*)k_outer<ITER_NW>, g, b, args, TVL1_RING_BYTES(ITER_NW), st);
+    if (e != cudaSuccess) return fail(TVL1_ERR_CUDA, "cooperative launch of k_outer failed: %s", cudaGetErrorString(e));
+    return TVL1_OK;
+}
+
 int launch_iterate2(IterArgs& a, cudaStream_t st)
 {
     int grid = 1;
@@ -312,6 +329,7 @@ struct tvl1_handle {
     tvl1_params prm;
     int inner = 30, outer = 10;
     bool timing = false;
+ bool coop_outer = true;             // fused levels: the inner loop of an outer iteration in ONE cooperative launch
     bool multi_iter = true;             // levels below fused_min_px: all inner iterations of an outer one in ONE cooperative launch
     long long fused_min_px = 1500000;   // levels at least this large use the two-iteration kernel (measured cross-over ~1.2 Mpx)
     // arena
@@ -573,7 +591,13 @@ static int calc_device(tvl1_handle* H, const uint8_t* f0, size_t pitch0, const u
                     const int left_pred = pred_total - done_total - done_inner;
                     want = want == 0 ? (left_pred + 1 > 4 ? left_pred + 1 : 4) : 2 * want;
                     if (want > H->inner - done_inner) want = H->inner - done_inner;
-                    if (fused) {
+                    if (fused && H->coop_outer) {
+                        // the whole inner loop of this outer iteration in one cooperative launch
+                        IterArgs io = ia;
+                        io.mode = 2;
+                        if ((rc = launch_outer(io, st))) return rc;
+                        launches += 1;
+                    } else if (fused) {
                         // temporally blocked schedule: [fused pair | single] slot pairs.  Which slot
                         // of a pair really runs is decided on the device: the pair while the stop is
                         // not imminent and two iterations still fit, the single after an overshoot
@@ -767,6 +791,7 @@ int tvl1_set_option(tvl1_handle* H, const char* key, double value)
     if (!H || !key) return fail(TVL1_ERR_INVALID, "null handle or key");
     if (!strcmp(key, "fused_min_px")) { H->fused_min_px = value < 0 ? 0 : (long long)value; return TVL1_OK; }
     if (!strcmp(key, "multi_iter")) { H->multi_iter = value != 0; return TVL1_OK; }
+    if (!strcmp(key, "coop_outer")) { H->coop_outer = value != 0; return TVL1_OK; }
     return fail(TVL1_ERR_INVALID, "unknown option '%s'", key);
 }
 

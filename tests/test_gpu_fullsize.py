@@ -42,7 +42,11 @@ def test_config1_8192_properties(gpu):
     u2, v2 = s.calc(I0, I1)
     assert np.array_equal(u, u2) and np.array_equal(v, v2)
     assert np.array_equal(it_fused, s.stats.iters_array())
-    # (2) one iteration per launch everywhere: identical to the temporally blocked schedule
+    # (2) the same passes as host-driven launch slots, and one iteration per launch everywhere: identical
+    s.set_option("coop_outer", 0)
+    u3, v3 = s.calc(I0, I1)
+    assert np.array_equal(it_fused, s.stats.iters_array())
+    assert np.array_equal(u, u3) and np.array_equal(v, v3)
     s.set_option("fused_min_px", 1e18)
     u3, v3 = s.calc(I0, I1)
     assert np.array_equal(it_fused, s.stats.iters_array())

@@ -1,6 +1,6 @@
 """Randomised parity: image sizes (odd, tiny, wide, tall), every solver parameter the reference's
 generate_TV_args exposes (src/optflow.cpp:500-514) plus scaleStep / inner / outer / medianFiltering, with
-and without zero bands, all three iteration schedules -- each case bit-exact against the oracle, iteration
+and without zero bands, all four iteration schedules -- each case bit-exact against the oracle, iteration
 counts included.  Seeds are fixed so that a failure reproduces."""
 import numpy as np
 import pytest
@@ -42,12 +42,13 @@ def test_random_config(gpu, orc, case):
         I0[:, -(w // 5):] = 0; I1[:, -(w // 5):] = 0
     okw = {("lambda" if k == "lambda_" else k): v for k, v in kw.items()}
     ou, ov, oit, olev = orc.tvl1_calc(I0, I1, **okw)
-    # every schedule: two iterations per launch everywhere / many iterations per cooperative launch /
-    # one iteration per launch
-    for fused_min, multi in ((0, 1), (1e18, 1), (1e18, 0)):
+    # every schedule: fused + single passes in one cooperative launch per outer iteration / the same passes
+    # as host-driven launch slots / single passes in one cooperative launch / one iteration per launch
+    for fused_min, multi, coop in ((0, 1, 1), (0, 1, 0), (1e18, 1, 1), (1e18, 0, 1)):
         s = gpu.Solver(gpu.default_params(**kw))
         s.set_option("fused_min_px", fused_min)
         s.set_option("multi_iter", multi)
+        s.set_option("coop_outer", coop)
         u, v = s.calc(I0, I1)
         assert s.stats.levels == olev, (case, kw)
         assert np.array_equal(s.stats.iters_array(), oit[:olev]), (case, kw, h, w)
