@@ -274,8 +274,21 @@ int launch_outer(IterArgs& a, cudaStream_t st)
 {
     int grid = 1, g1 = 1;
     const int resident = resident_blocks(KI_OUTER);
-    a.rows = tile_rows(a.w, a.h, TVL1_STRIP2, 3, 8, resident, &grid);
-    a.rows1 = tile_rows(a.w, a.h, TVL1_STRIP, 1, 4, resident, &g1);   // its single passes stride over the same grid
+    const long long slots = (long long)resident * ITER_NW;
+    const long long ns2 = cdiv(a.w, TVL1_STRIP2), ns1 = cdiv(a.w, TVL1_STRIP);
+    int R2 = 0, R1 = 0;
+    // small levels are bound by latency: the shortest tiles that still give every tile its own warp
+    for (int r = 1; r <= 8 && !R2; ++r)
+        if (ns2 * cdiv(a.h, r) <= slots) R2 = r;
+    for (int r = 1; r <= 8 && !R1; ++r)
+        if (ns1 * cdiv(a.h, r) <= slots) R1 = r;
+    if (R2) {
+        a.rows = R2;
+        grid = (int)((ns2 * cdiv(a.h, R2) + ITER_NW - 1) / ITER_NW);
+    } else {
+        a.rows = tile_rows(a.w, a.h, TVL1_STRIP2, 3, 8, resident, &grid);
+    }
+    a.rows1 = R1 ? R1 : tile_rows(a.w, a.h, TVL1_STRIP, 1, 4, resident, &g1);   // single passes stride over the same grid
     dim3 b(32, ITER_NW), g(grid);
     void* args[] = {(void*)&a};
     cudaError_t e = cudaLaunchCooperativeKernel((const void*)k_outer<ITER_NW>, g, b, args, TVL1_RING_BYTES(ITER_NW), st);
@@ -331,7 +344,7 @@ struct tvl1_handle {
     bool timing = false;
  bool coop_outer = true;             // fused levels: the inner loop of an outer iteration in ONE cooperative launch
     bool multi_iter = true;             // levels below fused_min_px: all inner iterations of an outer one in ONE cooperative launch
-    long long fused_min_px = 1500000;   // levels at least this large use the two-iteration kernel (measured cross-over ~1.2 Mpx)
+    long long fused_min_px = 0;         // levels at least this large use the two-iteration passes (with the cooperative loop they win at every size)
     // arena
     char* arena = nullptr;
     size_t arena_bytes = 0;

@@ -93,7 +93,7 @@ int tvl1_create(const tvl1_params* p, int device, tvl1_handle** out);
 void tvl1_destroy(tvl1_handle* h);
 int tvl1_set_params(tvl1_handle* h, const tvl1_params* p);
 /* Tuning knobs that never change results.  "fused_min_px": pyramid levels with at least this
- * many pixels run the temporally blocked two-iteration kernel (default 1.5e6; 0 = always,
+ * many pixels run the temporally blocked two-iteration passes (default 0 = always;
  * 1e18 = never).  "multi_iter": smaller levels run all inner iterations of an outer iteration in one
  * cooperative launch (default 1; 0 = one launch per iteration).  "coop_outer": the larger levels run
  * the inner loop of an outer iteration (two-iteration and single passes) in one cooperative launch
