@@ -13,9 +13,14 @@ One JSON line on stdout (rank 0):
   value     Mpx/s with the frames already resident in HBM (tvl1_calc_u8, CUDA events)
   e2e       Mpx/s through the host-buffer C-ABI call (tvl1_calc_u8_host): H2D of both frames
             from pinned memory and D2H of both flow planes inside the timed region
-  roofline  the primal-dual iteration kernels (k_iterate2: two iterations per launch, k_iterate: one):
-            64 B/px/iteration x the px-iterations executed / their CUDA-event time
-            inside the timed region (no-op launches and host read-backs of the stop flag included)
+  roofline  the primal-dual iteration kernel k_outer (one cooperative launch per outer iteration: its
+            two-iteration and single passes): 64 B/px/iteration x the px-iterations
+            executed / its CUDA-event time inside the timed region (host read-backs of the stop flag
+            included); `traffic` / `dram_frac` from the ncu capture of the same kernel (profiles/)
+  parity    CUDA path vs the C oracle on configs[0] (2048^2 pair), outside the timed regions:
+            mean / max endpoint error, iteration-count vector equality, bit-equality
+  stack     configs[2]: 512 chained 4096^2 pairs, strong-scaled over the N GPUs (tvl1_stack_run)
+  volume    configs[4]-style: chained 6144^2 slices per GPU, matches only (no flow download)
   cpu_baseline  the C oracle (oracle/, OpenMP) on a bounded crop of the same pair
 """
 import argparse
@@ -47,6 +52,9 @@ def workload(args):
             "tau": 0.25, "lambda": 0.15, "theta": 0.3, "epsilon": 0.01, "scaleStep": 0.8,
             "innerIterations": 30, "outerIterations": 10, "medianFiltering": 5,
             "pairs_per_gpu_per_step": 1, "sharding": "by pair, no collective",
+            "reference_arm_sample": "the CPU arm (--impl reference, cpu_baseline) solves the centre %dx%d crop of this "
+                                    "pair per step (bounded sample; Mpx/s of the crop)" % (
+                                        min(CPU_CROP, args.size), min(CPU_CROP, args.size)),
             "l2": "inputs larger than L2 (%.1f GB of planes per pair)" % (
                 args.size * args.size * 4 * 24 / 1e9)}
 
@@ -205,6 +213,7 @@ def run_ours(args):
     I0, I1 = make_pair(args, rank)
     solver = N.Solver(N.default_params(lambda_=0.15, nscales=args.scales, warps=args.warps,
                                        inner_iterations=30, outer_iterations=10), device=local)
+    solver.set_timing(True)     # per-stage CUDA events: the roofline's kernel time comes from them
     # device-resident inputs / outputs (torch only allocates and hands out pointers)
     d0 = torch.from_numpy(I0).cuda()
     d1 = torch.from_numpy(I1).cuda()
@@ -290,33 +299,101 @@ def run_ours(args):
     clocks = sampler.stop()
     checksum = float(hu[::257, ::263].double().sum() + hv[::257, ::263].double().sum())
 
-    # BASELINE configs[2] excerpt: a stack of chained 4096^2 slices per GPU through
-    # tvl1_stack_run (every slice uploaded once, uploads/downloads overlapped with the solves)
+    # ---- parity vs the oracle on configs[0] (outside every timed region; rank 0)
+    parity = None
+    if rank == 0 and not args.no_parity:
+        from oracle import oracle as O
+        P0, P1 = synth.make_pair(2048, 2048, seed=7)
+        ps = N.Solver(N.default_params(lambda_=0.15, nscales=5, warps=5, inner_iterations=30,
+                                       outer_iterations=10), device=local)
+        gu, gv = ps.calc(P0, P1)
+        ou, ov, oit, olev = O.tvl1_calc(P0, P1, **{"lambda": 0.15, "nscales": 5, "nthreads": os.cpu_count() or 1})
+        epe = np.hypot(gu - ou, gv - ov)
+        parity = {"config": "configs[0]: 2048x2048 pair, 5 scales, 5 warps, vs oracle/tvl1_oracle.c",
+                  "mean_epe": float(epe.mean()), "max_epe": float(epe.max()),
+                  "iters_equal": bool(ps.stats.levels == olev and np.array_equal(ps.stats.iters_array(), oit[:olev])),
+                  "bit_equal": bool(np.array_equal(gu, ou) and np.array_equal(gv, ov)),
+                  "bounds": {"mean_epe": 0.01, "max_epe": 0.1}}
+        ps.close()
+        del gu, gv, ou, ov, epe
+
+    def chained(n_distinct, size, seed):
+        """n_distinct+1 chained slices walked back and forth, so that ANY number of adjacent pairs can
+        be formed from a few pinned buffers (slice k+1 is always a neighbour of slice k)."""
+        sl = synth.make_stack(n_distinct, size, size, seed=seed)
+        return [torch.from_numpy(a).pin_memory() for a in sl]
+
+    def walk(n_slices, n_buf, start=0):
+        period = 2 * (n_buf - 1)
+        out = []
+        for k in range(n_slices):
+            r = (start + k) % period
+            out.append(r if r < n_buf else period - r)
+        return out
+
+    # ---- configs[2]: a stack of 512 chained 4096^2 pairs, STRONG-scaled: rank r solves its contiguous
+    # block of pairs through tvl1_stack_run (every slice uploaded once, uploads / flow downloads / match
+    # sampling overlapped with the solves; flows land in a ring of pinned host planes)
     stack = None
     if args.stack_pairs > 0:
         SS = args.stack_size
-        sl = synth.make_stack(args.stack_pairs, SS, SS, seed=100 + rank)
-        hs = [torch.from_numpy(a).pin_memory() for a in sl]
-        ou = [torch.empty((SS, SS), dtype=torch.float32).pin_memory() for _ in range(args.stack_pairs)]
-        ov = [torch.empty((SS, SS), dtype=torch.float32).pin_memory() for _ in range(args.stack_pairs)]
+        total = args.stack_pairs
+        lo = rank * total // world
+        hi = (rank + 1) * total // world
+        mine = hi - lo
+        hs = chained(8, SS, 100)
+        ring = [torch.empty((SS, SS), dtype=torch.float32).pin_memory() for _ in range(8)]
         st_solver = N.Solver(N.default_params(lambda_=0.15, nscales=5, warps=5, inner_iterations=30,
                                               outer_iterations=10), device=local)
-        kw = dict(slices=None, flows=True, apply_mask=True, npoints=25, scale=0.5, seed=1,
-                  out_u=[t.data_ptr() for t in ou], out_v=[t.data_ptr() for t in ov],
-                  slice_ptrs=[t.data_ptr() for t in hs], pitch=SS, shape=(SS, SS))
-        st_solver.run_stack(**kw)
+
+        def run(npairs, start):
+            idx = walk(npairs + 1, len(hs), start)
+            return st_solver.run_stack(slices=None, flows=True, apply_mask=True, npoints=25, scale=0.5, seed=1,
+                                       out_u=[ring[(2 * k) % 8].data_ptr() for k in range(npairs)],
+                                       out_v=[ring[(2 * k + 1) % 8].data_ptr() for k in range(npairs)],
+                                       slice_ptrs=[hs[i].data_ptr() for i in idx], pitch=SS, shape=(SS, SS))
+        run(3, 0)
         barrier()
         t0 = time.perf_counter()
-        r = st_solver.run_stack(**kw)
+        r = run(mine, lo) if mine > 0 else None
         barrier()
         ms_stack = allmax((time.perf_counter() - t0) * 1e3)
-        px_stack = allsum(float(SS) * SS * args.stack_pairs)
-        stack = {"workload": "configs[2] excerpt: %d chained %dx%d pairs per GPU, 5 scales, 5 warps, "
-                             "mask + 25 matches + flow download per pair" % (args.stack_pairs, SS, SS),
-                 "value": px_stack / (ms_stack * 1e-3) / 1e6, "unit": UNIT, "ms_per_pair": ms_stack / args.stack_pairs,
+        stack = {"workload": "configs[2]: stack of %d chained %dx%d pairs sharded by contiguous block over %d GPU(s), "
+                             "5 scales, 5 warps, mask + 25 matches + flow download per pair" % (total, SS, SS, world),
+                 "value": float(SS) * SS * total / (ms_stack * 1e-3) / 1e6, "unit": UNIT, "scaling": "strong",
+                 "pairs_total": total, "pairs_per_gpu": mine, "ms_per_pair_per_gpu": ms_stack / max(mine, 1),
+                 "h2d_bytes_per_pair": SS * SS, "d2h_bytes_per_pair": 8 * SS * SS,
                  "api": "tvl1_stack_run (pinned host buffers, copy streams)",
-                 "iterations_per_pair": [int(x.total_iterations) for x in r["stats"]]}
+                 "iterations_first_pairs": [int(x.total_iterations) for x in (r["stats"][:4] if r else [])]}
         st_solver.close()
+        del hs, ring
+
+    # ---- configs[4]-style: chained 6144^2 slices, matches only (flow never leaves the device)
+    volume = None
+    if args.volume_pairs > 0:
+        VS = args.volume_size
+        hs = chained(4, VS, 200 + rank)
+        v_solver = N.Solver(N.default_params(lambda_=0.15, nscales=5, warps=5, inner_iterations=30,
+                                             outer_iterations=10), device=local)
+
+        def runv(npairs):
+            idx = walk(npairs + 1, len(hs))
+            return v_solver.run_stack(slices=None, flows=False, apply_mask=True, npoints=25, scale=0.5, seed=1,
+                                      slice_ptrs=[hs[i].data_ptr() for i in idx], pitch=VS, shape=(VS, VS))
+        runv(2)
+        barrier()
+        t0 = time.perf_counter()
+        runv(args.volume_pairs)
+        barrier()
+        ms_vol = allmax((time.perf_counter() - t0) * 1e3)
+        volume = {"workload": "configs[4]-style: %d chained %dx%d pairs per GPU, 5 scales, 5 warps, mask + 25 matches "
+                              "per pair, no flow download (h_u = NULL)" % (args.volume_pairs, VS, VS),
+                  "value": allsum(float(VS) * VS * args.volume_pairs) / (ms_vol * 1e-3) / 1e6, "unit": UNIT,
+                  "scaling": "weak", "ms_per_pair": ms_vol / args.volume_pairs,
+                  "h2d_bytes_per_pair": VS * VS, "d2h_bytes_per_pair": 25 * 5 * 8,
+                  "api": "tvl1_stack_run (h_u = NULL)"}
+        v_solver.close()
+        del hs
 
     px_all = allsum(float(S) * S * K)
     total_launches = int(allsum(float(launches)))
@@ -329,13 +406,19 @@ def run_ours(args):
                 per_level.append({"level": l, "size": [w, h],
                                   "gbs": round(64.0 * lvl_pxit[l] / (lvl_ms[l] * 1e-3) / 1e9, 1),
                                   "ms": round(lvl_ms[l] / K, 3)})
-        traffic = traffic_kernel = None
-        tp = os.path.join(ROOT, "profiles", "k_iterate_traffic.json")
+        # DRAM traffic of the same kernel from its ncu --set full capture (profiles/k_outer_traffic.json:
+        # one level-0 k_outer launch of a known iteration count): per launch, and per px-iteration so
+        # that dram_frac can be formed from THIS run's kernel time
+        traffic = traffic_kernel = dram_frac = bytes_px_it = None
+        tp = os.path.join(ROOT, "profiles", "k_outer_traffic.json")
         if os.path.exists(tp):
             try:
                 tj = json.load(open(tp))
                 traffic = tj.get("dram_bytes_per_launch")
                 traffic_kernel = tj.get("kernel")
+                bytes_px_it = tj.get("dram_bytes_per_px_iteration")
+                if bytes_px_it and it_ms > 0:
+                    dram_frac = bytes_px_it * it_px / (it_ms * 1e-3) / 1e9 / peak
             except Exception:
                 traffic = None
         line = {
@@ -349,18 +432,20 @@ def run_ours(args):
                     "checksum": checksum},
             "gpu_launches": total_launches,
             "roofline": {"bound": "hbm",
-                         "kernel": "k_iterate2 + k_iterate (primal-dual iterations, all levels, inside the timed region)",
+                         "kernel": "k_outer<4> (primal-dual iterations: its two-iteration and single passes, one "
+                                   "cooperative launch per outer iteration, all levels, inside the timed region)",
                          "achieved": ach, "peak": peak, "unit": "GB/s",
                          "frac": ach / peak if peak else None, "traffic": traffic,
+                         "dram_frac": dram_frac, "dram_bytes_per_px_iteration": bytes_px_it,
                          "peak_source": peak_src, "copy_gbs_this_box": copy_gbs,
                          "frac_of_this_box_copy": (ach / copy_gbs) if copy_gbs else None,
                          "bytes_per_px_iteration": 64,
                          "px_iterations_per_step": it_px / K, "kernel_ms_per_step": it_ms / K,
                          "traffic_kernel": traffic_kernel,
-                         "launch_bytes_level0": 2 * 64.0 * levels[0][0] * levels[0][1],
-                         "launch_bytes_note": "k_iterate2 advances two iterations per launch: 128 B/px algorithmic, "
-                                              "60 B/px compulsory (9 planes read + 6 written once); frac > 1 is what "
-                                              "temporal blocking is for -- `traffic` is the DRAM bytes ncu measured",
+                         "note": "frac = 64 B/px/iteration model / measured copy peak: a two-iteration pass moves 60 B/px "
+                                 "for TWO iterations (9 planes read + 6 written once), so frac > 1 is what temporal "
+                                 "blocking is for; dram_frac = DRAM bytes ncu measured per px-iteration x this run's "
+                                 "px-iterations / this run's kernel time / peak",
                          "per_level": per_level,
                          "pair_algorithmic_gbs": alg_bytes / (ms_dev / K * 1e-3) / 1e9},
             "clocks": clocks,
@@ -369,8 +454,12 @@ def run_ours(args):
                                    "warp": stats.ms_warp, "iterate": stats.ms_iterate,
                                    "median": stats.ms_median, "other": stats.ms_other},
         }
+        if parity is not None:
+            line["parity"] = parity
         if stack is not None:
             line["stack"] = stack
+        if volume is not None:
+            line["volume"] = volume
         if world == 1 and not args.no_cpu:
             cb = cpu_leg(args, 1, 0)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
@@ -392,8 +481,11 @@ def main():
     ap.add_argument("--scales", type=int, default=6)
     ap.add_argument("--warps", type=int, default=5)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--stack-pairs", type=int, default=6, help="extra leg: pairs per GPU of the stack excerpt (0 = off)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the parity leg (configs[0] vs the oracle)")
+    ap.add_argument("--stack-pairs", type=int, default=512, help="configs[2] leg: pairs of the whole stack, split over the GPUs (0 = off)")
     ap.add_argument("--stack-size", type=int, default=4096)
+    ap.add_argument("--volume-pairs", type=int, default=16, help="configs[4] leg: pairs per GPU, matches only (0 = off)")
+    ap.add_argument("--volume-size", type=int, default=6144)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

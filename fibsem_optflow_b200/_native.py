@@ -73,7 +73,7 @@ EXPORTS = [
     "tvl1_set_params", "tvl1_set_option", "tvl1_set_timing", "tvl1_calc_u8", "tvl1_calc_u8_host",
     "tvl1_prescaled_size", "tvl1_prescale_u8", "tvl1_prescale_u8_host",
     "tvl1_mask_flow_u8", "tvl1_sample_matches", "tvl1_sample_matches_skip", "tvl1_stack_run", "tvl1_k_convert_u8", "tvl1_k_resize",
-    "tvl1_k_centered_gradient", "tvl1_k_warp", "tvl1_k_iterate", "tvl1_k_iterate_fused2", "tvl1_k_median5", "tvl1_k_last_ms",
+    "tvl1_k_centered_gradient", "tvl1_k_warp", "tvl1_k_iterate", "tvl1_k_iterate_fused2", "tvl1_k_outer", "tvl1_k_median5", "tvl1_k_last_ms",
     "tvl1_pyramid_sizes", "tvl1_glibc_rand", "tvl1_selftest_arith", "tvl1_dev_count", "tvl1_dev_alloc", "tvl1_dev_free",
     "tvl1_dev_memset", "tvl1_dev_h2d", "tvl1_dev_d2h", "tvl1_dev_sync",
     "tvl1_host_alloc_pinned", "tvl1_host_free_pinned",
@@ -129,6 +129,7 @@ def lib():
     L.tvl1_k_iterate.argtypes = [_vp] * 10 + [C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
                                               C.c_float, C.c_int, _vp, _vp]
     L.tvl1_k_iterate_fused2.argtypes = L.tvl1_k_iterate.argtypes
+    L.tvl1_k_outer.argtypes = L.tvl1_k_iterate.argtypes
     L.tvl1_prescaled_size.argtypes = [C.c_int, C.c_int, C.c_double, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.tvl1_prescale_u8.argtypes = [_vp, _sz, C.c_int, C.c_int, C.c_double, _vp, _sz, _vp]
     L.tvl1_prescale_u8_host.argtypes = [C.c_int, _vp, _sz, C.c_int, C.c_int, C.c_double, _vp, _sz]
@@ -307,6 +308,10 @@ class Solver:
     def set_option(self, key, value):
         check(lib().tvl1_set_option(self.handle, key.encode(), float(value)))
 
+    def set_timing(self, enabled=True):
+        """Per-stage CUDA-event times in `stats` (off by default: only ms_total is measured)."""
+        check(lib().tvl1_set_timing(self.handle, int(bool(enabled))))
+
     def set_params(self, params):
         check(lib().tvl1_set_params(self.handle, C.byref(params)))
         self.params = params
@@ -467,12 +472,13 @@ def k_warp(I0, I1, u1, u2, device=0):
 
 def k_iterate(I1wx, I1wy, grad, rho_c, u1, u2, p11, p12, p21, p22, l_t, theta, taut, n=1, device=0,
               fused=False):
-    """n iterations; returns (u1,u2,p11,p12,p21,p22, errors[n]).  fused: two per launch."""
+    """n iterations; returns (u1,u2,p11,p12,p21,p22, errors[n]).  fused: two per launch;
+    fused="outer": all n in one cooperative k_outer launch (the shipped schedule)."""
     h, w = np.asarray(u1).shape
     consts = [Plane(h, w, device, np.asarray(a, np.float32)) for a in (I1wx, I1wy, grad, rho_c)]
     state = [Plane(h, w, device, np.asarray(a, np.float32)) for a in (u1, u2, p11, p12, p21, p22)]
     errs = np.zeros(max(n, 1), np.float64)
-    fn = lib().tvl1_k_iterate_fused2 if fused else lib().tvl1_k_iterate
+    fn = lib().tvl1_k_outer if fused == "outer" else (lib().tvl1_k_iterate_fused2 if fused else lib().tvl1_k_iterate)
     check(fn(*[p.ptr for p in consts], *[p.ptr for p in state], w, h,
              state[0].pitch, l_t, theta, taut, n, errs.ctypes.data, None))
     return tuple(p.get() for p in state) + (errs[:n],)

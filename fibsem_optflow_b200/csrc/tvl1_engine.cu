@@ -182,7 +182,15 @@ static int resident_blocks(int which)
     return c;
 }
 
-size_t iterate_max_blocks(int, int) { return 148 * 32 * 2; }
+// upper bound of the grid of any iteration kernel (blocks resident on the device), for the
+// per-block partial sums: SMs x the 32-blocks-per-SM hardware limit, two slabs
+size_t iterate_max_blocks()
+{
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return (size_t)sms * 32 * 2;
+}
 
 // Rows per tile and grid size.  A tile is one warp's strip x R rows and every resident warp walks
 // the tile list with a grid stride: tall tiles amortise the halo rows (R / (R + halo)), but the
@@ -404,7 +412,7 @@ static void release_arena(tvl1_handle* H)
     H->cap_w = H->cap_h = 0;
 }
 
-static int ensure_capacity(tvl1_handle* H, int w, int h)
+static int ensure_capacity(tvl1_handle* H, int w, int h, cudaStream_t st)
 {
     if (H->arena && H->cap_w == w && H->cap_h == h && H->cap_scales == H->prm.nscales &&
         H->cap_step == H->prm.scale_step)
@@ -426,7 +434,7 @@ static int ensure_capacity(tvl1_handle* H, int w, int h)
     size_t o_scr[5], o_p[8];
     for (int i = 0; i < 5; i++) o_scr[i] = carve(b0);   // I1wx I1wy rho u1x u2x
     for (int i = 0; i < 8; i++) o_p[i] = carve(b0);
-    const size_t nb = iterate_max_blocks(w, h);
+    const size_t nb = iterate_max_blocks();
     const size_t o_part = carve(nb * sizeof(double));
     const size_t o_ctrl = carve(sizeof(Ctrl));
     cudaError_t e = cudaMalloc(&H->arena, off);
@@ -449,8 +457,9 @@ static int ensure_capacity(tvl1_handle* H, int w, int h)
     H->partials_cap = nb;
     H->d_ctrl = (Ctrl*)(H->arena + o_ctrl);
     H->cap_w = w; H->cap_h = h; H->cap_scales = H->prm.nscales; H->cap_step = H->prm.scale_step;
-    // pad columns are read (never used) by the vectorised kernels: give them defined contents
-    CK(cudaMemset(H->arena, 0, off));
+    // pad columns are read (never used) by the vectorised kernels: give them defined contents.  On the
+    // solve's own stream: a non-blocking stream does not order itself after the legacy default stream
+    CK(cudaMemsetAsync(H->arena, 0, off, st));
     return TVL1_OK;
 }
 
@@ -497,7 +506,7 @@ static int calc_device(tvl1_handle* H, const uint8_t* f0, size_t pitch0, const u
         return fail(TVL1_ERR_INVALID, "pitch smaller than a row");
     CK(cudaSetDevice(H->device));
     int rc;
-    if ((rc = ensure_capacity(H, w, h))) return rc;
+    if ((rc = ensure_capacity(H, w, h, st))) return rc;
     if ((rc = upload_cubic_table(H->device))) return rc;
     const tvl1_params& P = H->prm;
     const int L = H->nlevels, W = P.warps;
@@ -511,7 +520,11 @@ static int calc_device(tvl1_handle* H, const uint8_t* f0, size_t pitch0, const u
     if ((rc = get_event(H, &ev_begin)) || (rc = get_event(H, &ev_pyr)) || (rc = get_event(H, &ev_end))) return rc;
     struct Span { cudaEvent_t a, b; int kind, level; };
     std::vector<Span> spans;
+    // per-stage events only when the caller asked for them (tvl1_set_timing): thousands of
+    // cudaEventRecord calls per pair otherwise
+    const bool timed = stats != nullptr && H->timing;
     auto span_begin = [&](int kind, int level) -> int {
+        if (!timed) return TVL1_OK;
         Span s; s.kind = kind; s.level = level;
         int r = get_event(H, &s.a); if (r) return r;
         r = get_event(H, &s.b); if (r) return r;
@@ -519,7 +532,7 @@ static int calc_device(tvl1_handle* H, const uint8_t* f0, size_t pitch0, const u
         spans.push_back(s);
         return TVL1_OK;
     };
-    auto span_end = [&]() { cudaEventRecord(spans.back().b, st); };
+    auto span_end = [&]() { if (timed) cudaEventRecord(spans.back().b, st); };
 
     CK(cudaEventRecord(ev_begin, st));
     CK(cudaMemsetAsync(H->d_ctrl, 0, sizeof(Ctrl), st));
@@ -544,6 +557,7 @@ static int calc_device(tvl1_handle* H, const uint8_t* f0, size_t pitch0, const u
     std::vector<int> counts((size_t)L * W, 0);   // iterations each (level, warp) needed
     double* dev_errlog = nullptr;                // developer aid: per-iteration error sums to stderr
     if (getenv("TVL1_DEV_ERRLOG")) cudaMalloc(&dev_errlog, sizeof(double) * L * W * H->inner * H->outer);
+    struct ErrlogGuard { double*& p; ~ErrlogGuard() { if (p) cudaFree(p); p = nullptr; } } errlog_guard{dev_errlog};
     for (int s = L - 1; s >= 0; --s) {
         const Level& lv = H->lv[s];
         const size_t pb = (size_t)lv.pitch * lv.h * sizeof(float);
@@ -654,7 +668,7 @@ static int calc_device(tvl1_handle* H, const uint8_t* f0, size_t pitch0, const u
                 fprintf(stderr, "\n");
             }
         }
-        if (s == 0) { if (dev_errlog) cudaFree(dev_errlog); break; }
+        if (s == 0) break;
         // flow upsample to the next finer level (A.2): resize to its size, times 1/scaleStep
         const Level& up = H->lv[s - 1];
         const int uc = H->h_ctrl->ucur[s];
@@ -925,9 +939,13 @@ int tvl1_stack_run(tvl1_handle* H, const tvl1_stack_io* io, float* ms_total)
     cudaStream_t cs = H->own_stream;
     const size_t p8 = H->st_pitch8;
     const int cap = io->npoints > 0 ? io->npoints : 1;
-    cudaEvent_t t0, t1;
-    CK(cudaEventCreate(&t0));
-    CK(cudaEventCreate(&t1));
+    struct EventPair {
+        cudaEvent_t a = nullptr, b = nullptr;
+        ~EventPair() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+    } tev;
+    CK(cudaEventCreate(&tev.a));
+    CK(cudaEventCreate(&tev.b));
+    cudaEvent_t t0 = tev.a, t1 = tev.b;
     CK(cudaEventRecord(t0, cs));
     auto upload = [&](int k) -> int {
         const int s = k % 3;
@@ -989,8 +1007,6 @@ int tvl1_stack_run(tvl1_handle* H, const tvl1_stack_io* io, float* ms_total)
     float ms = 0.f;
     cudaEventElapsedTime(&ms, t0, t1);
     if (ms_total) *ms_total = ms;
-    cudaEventDestroy(t0);
-    cudaEventDestroy(t1);
     return TVL1_OK;
 }
 
@@ -1063,7 +1079,7 @@ static int k_iterate_impl(int fused, const float* d_I1wx, const float* d_I1wy, c
     if (n > TVL1_MAX_LEVELS * TVL1_MAX_WARPS) return fail(TVL1_ERR_INVALID, "n too large");
     cudaStream_t st = (cudaStream_t)stream;
     const size_t pb = (size_t)pitch * h * sizeof(float);
-    const size_t nb = iterate_max_blocks(w, h);
+    const size_t nb = iterate_max_blocks();
     char* tmp = nullptr;
     const size_t ctrl_off = 6 * pb, part_off = ctrl_off + 1024 * ((sizeof(Ctrl) + 1023) / 1024);
     const size_t log_off = part_off + nb * sizeof(double);
@@ -1086,10 +1102,17 @@ static int k_iterate_impl(int fused, const float* d_I1wx, const float* d_I1wy, c
     a.errlog = (double*)(tmp + log_off);
     int rc = TVL1_OK;
     stage_begin(st);
-    if (fused) { for (int i = 0; i + 1 < n && !rc; i += 2) rc = launch_iterate2(a, st); }
+    if (fused == 2) {
+        // the shipped schedule: ONE cooperative k_outer launch runs all n iterations (two-iteration
+        // passes, plus one single pass when n is odd); scaled_eps < 0 keeps the stop test from firing
+        a.mode = 2; a.inner_max = n;
+        if (n > 0) rc = launch_outer(a, st);
+    } else if (fused) { for (int i = 0; i + 1 < n && !rc; i += 2) rc = launch_iterate2(a, st); }
     else { for (int i = 0; i < n && !rc; i++) rc = launch_iterate(a, st); }
     stage_end(st);
-    if (!rc && ((fused ? n / 2 : n) & 1)) {
+    // passes made = buffer flips: n single passes, n/2 fused ones, n/2 + n%2 inside k_outer
+    const int flips = fused == 2 ? n / 2 + (n & 1) : (fused ? n / 2 : n);
+    if (!rc && (flips & 1)) {
         float* dst[6] = {d_u1, d_u2, d_p11, d_p12, d_p21, d_p22};
         for (int k = 0; k < 6 && !rc; k++)
             if (cudaMemcpyAsync(dst[k], tw[k], pb, cudaMemcpyDeviceToDevice, st) != cudaSuccess)
@@ -1119,6 +1142,14 @@ int tvl1_k_iterate_fused2(const float* d_I1wx, const float* d_I1wy, const float*
 {
     if (n & 1) return fail(TVL1_ERR_INVALID, "the fused kernel advances two iterations per launch: n must be even");
     return k_iterate_impl(1, d_I1wx, d_I1wy, d_grad, d_rho_c, d_u1, d_u2, d_p11, d_p12, d_p21, d_p22, w, h, pitch,
+                          l_t, theta, taut, n, errors, stream);
+}
+
+int tvl1_k_outer(const float* d_I1wx, const float* d_I1wy, const float* d_grad, const float* d_rho_c,
+                 float* d_u1, float* d_u2, float* d_p11, float* d_p12, float* d_p21, float* d_p22,
+                 int w, int h, int pitch, float l_t, float theta, float taut, int n, double* errors, void* stream)
+{
+    return k_iterate_impl(2, d_I1wx, d_I1wy, d_grad, d_rho_c, d_u1, d_u2, d_p11, d_p12, d_p21, d_p22, w, h, pitch,
                           l_t, theta, taut, n, errors, stream);
 }
 

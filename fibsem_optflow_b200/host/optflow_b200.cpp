@@ -30,6 +30,7 @@
 #include <future>
 #include <iostream>
 #include <map>
+#include <stdexcept>
 #include <string>
 #include <vector>
 
@@ -57,6 +58,8 @@ struct Driver {
     DeviceFrame d0, d1, du, dv;
     long long rand_skip = 0;   // debug mode: one rand() stream for the whole process
     int uploads = 0;
+    int shard = 0, nshards = 1, skipped = 0;
+    mj::Value all_matches = mj::Value::array();   // every batch so far, for the "matches_file" key
 
     ~Driver()
     {
@@ -72,9 +75,15 @@ struct Driver {
     std::exit(2);
 }
 
+// A problem with ONE pair (roi outside the frame, frames of different size, a solver status): the pair
+// is logged and skipped and the job goes on, as the reference does for an unreadable image
+// (src/optflow.cpp:108-112, 120-124); matches already batched are still flushed at the end.
+struct PairError : std::runtime_error { using std::runtime_error::runtime_error; };
+[[noreturn]] void pair_fail(const std::string& m) { throw PairError(m); }
+
 void ck(int rc, const char* what)
 {
-    if (rc < 0) die(std::string(what) + ": " + tvl1_last_error());
+    if (rc < 0) pair_fail(std::string(what) + ": " + tvl1_last_error());
 }
 
 const Value& pick(const Value& im, const Value& args, const char* key, const Value& dflt)
@@ -138,7 +147,7 @@ void ensure_solver(Driver& D, const tvl1_params& p)
 
 Rect roi_from_array(const Value& a)
 {
-    if (!a.isArray() || a.size() < 4) die("an roi must be [x, y, width, height]");
+    if (!a.isArray() || a.size() < 4) pair_fail("an roi must be [x, y, width, height]");
     return Rect{(int)a[0].asInt(), (int)a[1].asInt(), (int)a[2].asInt(), (int)a[3].asInt()};
 }
 
@@ -158,7 +167,7 @@ void get_rois(Value& rois, const Value& spec, int rows, int cols)
     if (spec.isMember("custom")) {
         const Value& c = spec.at("custom");
         if (c.isMember("0")) {
-            if (!c.isMember("1")) die("rois.custom with \"0\" needs \"1\" as well");
+            if (!c.isMember("1")) pair_fail("rois.custom with \"0\" needs \"1\" as well");
             rois["custom_diff"]["0"] = c.at("0");
             rois["custom_diff"]["1"] = c.at("1");
         } else {
@@ -170,14 +179,14 @@ void get_rois(Value& rois, const Value& spec, int rows, int cols)
 void check_roi(const Rect& r, int w, int h, const char* which)
 {
     if (r.w <= 0 || r.h <= 0 || r.x < 0 || r.y < 0 || r.x + r.w > w || r.y + r.h > h)
-        die(std::string("roi outside the frame (") + which + ")");
+        pair_fail(std::string("roi outside the frame (") + which + ")");
 }
 
 // solve_wrapper (src/optflow.cpp:395-497), features == false
 void solve_wrapper(Driver& D, const imio::Gray8& f0, const imio::Gray8& f1, const Rect& r0, const Rect& r1,
                    Value& im, const Value& args)
 {
-    if (r0.w != r1.w || r0.h != r1.h) die("the two rois of a pair must have the same size");
+    if (r0.w != r1.w || r0.h != r1.h) pair_fail("the two rois of a pair must have the same size");
     const int w = r0.w, h = r0.h;
     ensure_solver(D, tv_params(im, args));
     reserve(D, D.du, (size_t)w * h * 4);
@@ -233,7 +242,7 @@ void solve_wrapper(Driver& D, const imio::Gray8& f0, const imio::Gray8& f1, cons
     }
     const std::string base = im.at("output").asString() + im.at("output_suffix").asString();
     if (!imio::write_tiff_f32(base + "_x.tiff", fx.data(), w, h) || !imio::write_tiff_f32(base + "_y.tiff", fy.data(), w, h))
-        die("cannot write " + base + "_{x,y}.tiff");
+        pair_fail("cannot write " + base + "_{x,y}.tiff");
 }
 
 // move_pm (src/optflow.cpp:574-593)
@@ -252,15 +261,35 @@ void move_pm(Value& im, Value& args)
 // upload_points (src/optflow.cpp:595-641): same payload, written to a file instead of PUT
 void upload_points(Driver& D, Value& args)
 {
+    // One file per batch, named by shard and batch so that the ranks of a sharded job (one process per
+    // GPU) never write the same name: point_matches_NNN.json, or point_matches_rRofW_NNN.json under
+    // --shard R/W.  The optional "matches_file" key collects EVERY batch of this process in one JSON
+    // array (rewritten after each batch; "<file>.rRofW" under --shard).
     const std::string dir = args.get("output_dir", Value(".")).asString();
-    char name[64];
-    std::snprintf(name, sizeof(name), "/point_matches_%03d.json", D.uploads++);
-    const std::string path = args.get("matches_file", Value(dir + name)).asString();
+    char name[96];
+    if (D.nshards > 1) std::snprintf(name, sizeof(name), "/point_matches_r%dof%d_%03d.json", D.shard, D.nshards, D.uploads++);
+    else std::snprintf(name, sizeof(name), "/point_matches_%03d.json", D.uploads++);
     const std::string payload = mj::dump(args.at("point_matches"));
-    FILE* f = std::fopen(path.c_str(), "wb");
-    if (!f) die("cannot write " + path);
-    std::fwrite(payload.data(), 1, payload.size(), f);
-    std::fclose(f);
+    auto write_all = [](const std::string& path, const std::string& text) {
+        FILE* f = std::fopen(path.c_str(), "wb");
+        if (!f) die("cannot write " + path);
+        std::fwrite(text.data(), 1, text.size(), f);
+        std::fclose(f);
+    };
+    std::string path = dir + name;
+    if (args.isMember("matches_file")) {
+        path = args.at("matches_file").asString();
+        if (D.nshards > 1) {
+            char suf[48];
+            std::snprintf(suf, sizeof(suf), ".r%dof%d", D.shard, D.nshards);
+            path += suf;
+        }
+        const Value& batch = args.at("point_matches");
+        for (size_t k = 0; k < batch.size(); k++) D.all_matches.append(batch[k]);
+        write_all(path, mj::dump(D.all_matches));
+    } else {
+        write_all(path, payload);
+    }
     if (args.get("debug", Value(false)).asBool()) {
         std::cout << payload << "\n";
         std::cout << "http://" << args.get("host", Value("10.40.3.162")).asString() << ":" << args.get("port", Value("8080")).asString()
@@ -299,8 +328,12 @@ bool finish_frame(int device, const std::string& path, Decoded&& d, float scale,
 // solve_rois (src/optflow.cpp:312-392)
 void solve_rois(Driver& D, const imio::Gray8& f0, const imio::Gray8& f1, const Value& rois, Value& im, Value& args)
 {
-    const bool want_features = (im.isMember("features") ? im.at("features").asBool() : args.get("features", Value(false)).asBool());
-    if (want_features) die("\"features\" (ORB/SURF pre-alignment) is not part of this build");
+    // src/optflow.cpp:323-338: an explicit false at either level wins, then a true at either level
+    bool want_features;
+    if (im.isMember("features") && !im.at("features").asBool()) want_features = false;
+    else if (args.isMember("features") && !args.at("features").asBool()) want_features = false;
+    else want_features = im.get("features", Value(false)).asBool() || args.get("features", Value(false)).asBool();
+    if (want_features) pair_fail("\"features\" (ORB/SURF pre-alignment) is not part of this build");
     reserve(D, D.d0, f0.px.size());
     reserve(D, D.d1, f1.px.size());
     ck(tvl1_dev_h2d(D.d0.ptr, f0.px.data(), f0.px.size()), "upload");
@@ -314,7 +347,7 @@ void solve_rois(Driver& D, const imio::Gray8& f0, const imio::Gray8& f1, const V
             check_roi(r1, f1.w, f1.h, "custom 1");
             solve_wrapper(D, f0, f1, r0, r1, im, args);
         } else {
-            if (f0.w != f1.w || f0.h != f1.h) die("frames of different size need the feature pre-alignment, which is not part of this build");
+            if (f0.w != f1.w || f0.h != f1.h) pair_fail("frames of different size need the feature pre-alignment, which is not part of this build");
             if (key == "default")
                 std::cerr << "note: no roi given; the reference would pre-align with features here, this build solves the whole frame as is\n";
             const Rect r = roi_from_array(kv.second);
@@ -334,7 +367,6 @@ int from_file(Driver& D, Value& args, int shard, int nshards)
     // (q of pair i-1 == p of pair i) is not decoded twice (:97-103); same idea, two cache slots
     struct Cached { std::string name; float scale = -1.f; imio::Gray8 img; };
     Cached cache[2];
-    long long last_upload = 0;
     bool any_upload_since = false;
     std::map<std::string, std::future<Decoded>> inflight;   // frames being decoded for the next pair
     auto prefetch = [&](const std::string& name) {
@@ -343,6 +375,8 @@ int from_file(Driver& D, Value& args, int shard, int nshards)
     const size_t n = images.size();
     const size_t base = n / nshards, rem = n % nshards;
     const size_t begin = shard * base + std::min<size_t>(shard, rem), end = begin + base + ((size_t)shard < rem ? 1 : 0);
+    long long last_upload = (long long)begin;   // the batch counter starts where this shard starts
+    D.shard = shard; D.nshards = nshards;
     for (size_t i = begin; i < end; i++) {
         Value im = images[i];
         const std::string n0 = im.at("p").asString(), n1 = im.at("q").asString();
@@ -359,6 +393,7 @@ int from_file(Driver& D, Value& args, int shard, int nshards)
             else d = decode_frame(name);
             return finish_frame(D.device, name, std::move(d), scale, out);
         };
+        try {
         const bool have = fetch(n0, frame0) && fetch(n1, frame1);
         // decode what the next pairs will need on host threads while this one is solved (decoding an
         // 8k x 8k PNG takes far longer than its solve, so the look-ahead -- not the GPU -- sets the pace
@@ -393,6 +428,12 @@ int from_file(Driver& D, Value& args, int shard, int nshards)
         if (!im.isMember("output"))
             im["output"] = Value(args.at("output_dir").asString() + "/" + im.at("output_name").asString() + "_" + buffer);
         solve_rois(D, frame0, frame1, rois, im, args);
+        } catch (const std::exception& e) {   // PairError, or a missing / mistyped key of this pair
+            std::cout << "Error: pair " << n0 << " " << n1 << " skipped (" << e.what() << ")\n";
+            std::cerr << "optflow_b200: pair " << i << " skipped: " << e.what() << "\n";
+            D.skipped++;
+            continue;
+        }
 
         if (pick(im, args, "output_type", Value("map")).asString() == "random_points") {
             any_upload_since = true;

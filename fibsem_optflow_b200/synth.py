@@ -35,10 +35,20 @@ def _cr(t):
             -1.5 * t3 + 2.0 * t2 + 0.5 * t, 0.5 * t3 - 0.5 * t2)
 
 
-def texture(h, w, seed, sigma=2.0):
-    """float32 canvas in [0,255], band-limited."""
+def texture(h, w, seed, sigma=2.0, coarse=0):
+    """float32 canvas in [0,255], band-limited.  coarse = f > 1 adds a second band of structure f times
+    larger (noise drawn on an f-times coarser grid, blurred there, repeated f times, then blurred with
+    the fine band): what a pyramid needs to recover displacements of many pixels (configs[3])."""
     rng = np.random.default_rng(seed)
     a = rng.integers(0, 256, size=(h, w), dtype=np.uint8).astype(np.float32)
+    if coarse and coarse > 1:
+        f = int(coarse)
+        hc, wc = (h + f - 1) // f, (w + f - 1) // f
+        c = rng.integers(0, 256, size=(hc, wc), dtype=np.uint8).astype(np.float32)
+        c = _blur(c, 1.0)
+        c = np.repeat(np.repeat(c, f, axis=0), f, axis=1)[:h, :w]
+        # equal contrast per band after the blur below: white noise loses ~ 1 / (2 sigma sqrt(pi)) of its std
+        a += c * np.float32(1.0 / (2.0 * sigma * np.sqrt(np.pi)) * 2.0)
     a = _blur(a, sigma)
     lo, hi = float(a.min()), float(a.max())
     a -= lo
@@ -72,11 +82,11 @@ def to_u8(a):
     return np.clip(np.rint(a), 0, 255).astype(np.uint8)
 
 
-def make_pair(h, w, seed=7, dx=1.3, dy=-0.7, shear=0.002, sigma=2.0, margin=32):
+def make_pair(h, w, seed=7, dx=1.3, dy=-0.7, shear=0.002, sigma=2.0, margin=32, coarse=0):
     """Returns (I0, I1) uint8 with I1(x, y) = I0(x + dx + shear*y', y + dy) (y' in canvas
     rows), i.e. the true flow from I0 to I1 is u = -(dx + shear*y'), v = -dy."""
     H, W = h + 2 * margin, w + 2 * margin
-    c = texture(H, W, seed, sigma)
+    c = texture(H, W, seed, sigma, coarse)
     m = shift_shear(c, dx, dy, shear)
     sl = (slice(margin, margin + h), slice(margin, margin + w))
     return to_u8(c[sl]), to_u8(m[sl])

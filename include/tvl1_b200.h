@@ -99,7 +99,8 @@ int tvl1_set_params(tvl1_handle* h, const tvl1_params* p);
  * the inner loop of an outer iteration (two-iteration and single passes) in one cooperative launch
  * (default 1; 0 = host-driven launch slots). */
 int tvl1_set_option(tvl1_handle* h, const char* key, double value);
-/* per-stage CUDA-event timing in tvl1_stats (adds stream syncs); default off */
+/* per-stage CUDA-event timing (ms_pyramid, ms_warp, ms_iterate[_level], ms_median, ms_other of
+ * tvl1_stats; two events per stage span).  Default off: only ms_total is measured. */
 int tvl1_set_timing(tvl1_handle* h, int enabled);
 
 /* Flow from frame0 to frame1 (device pointers).  stream is a cudaStream_t (may be 0).
@@ -214,6 +215,12 @@ int tvl1_k_iterate_fused2(const float* d_I1wx, const float* d_I1wy, const float*
                           const float* d_rho_c, float* d_u1, float* d_u2, float* d_p11, float* d_p12,
                           float* d_p21, float* d_p22, int w, int h, int pitch,
                           float l_t, float theta, float taut, int n, double* errors, void* stream);
+/* same through k_outer, the kernel the solver ships: all n iterations (any n >= 0) in ONE cooperative
+ * launch -- two-iteration passes and, for odd n, a final single pass */
+int tvl1_k_outer(const float* d_I1wx, const float* d_I1wy, const float* d_grad,
+                 const float* d_rho_c, float* d_u1, float* d_u2, float* d_p11, float* d_p12,
+                 float* d_p21, float* d_p22, int w, int h, int pitch,
+                 float l_t, float theta, float taut, int n, double* errors, void* stream);
 int tvl1_k_median5(const float* d_src, int w, int h, int pitch, float* d_dst, void* stream);
 /* CUDA-event time of the kernel launches of the calling thread's most recent tvl1_k_warp /
  * tvl1_k_iterate / tvl1_k_median5 call (waits for them). */

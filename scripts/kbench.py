@@ -1,5 +1,5 @@
 """Developer micro-benchmark of single stage kernels through the stage-level C ABI.
-usage: python scripts/kbench.py <warp|median|iterate|all> [size] [reps]"""
+usage: python scripts/kbench.py <warp|median|iterate|outer|all> [size] [reps]"""
 import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -64,6 +64,18 @@ def main():
             best = min(best, N.k_last_ms() / 40)
         dt = best * 1e-3
         print(f"k_iterate2 {n}^2: {dt*1e6:.1f} us/iter  {64*px/dt/1e9:.0f} GB/s (64 B/px model)")
+    if which in ("outer", "iterate", "all"):
+        # the shipped kernel: NIT iterations in ONE cooperative k_outer launch
+        NIT = int(os.environ.get("KB_OUTER_ITERS", 30))
+        if which == "outer":
+            p = [N.Plane(n, n) for _ in range(4)]
+        best = 1e9
+        for _ in range(reps if which == "outer" else 3):
+            N.check(L.tvl1_k_outer(outs[0].ptr, outs[1].ptr, outs[0].ptr, outs[2].ptr, u1.ptr, u2.ptr, p[0].ptr, p[1].ptr,
+                                   p[2].ptr, p[3].ptr, n, n, u1.pitch, 0.045, 0.3, 0.25 / 0.3, NIT, None, None))
+            best = min(best, N.k_last_ms() / NIT)
+        dt = best * 1e-3
+        print(f"k_outer   {n}^2 ({NIT} iterations per launch): {dt*1e6:.1f} us/iter  {64*px/dt/1e9:.0f} GB/s (64 B/px model)")
 
 if __name__ == "__main__":
     main()

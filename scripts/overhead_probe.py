@@ -9,6 +9,7 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
 I0, I1 = synth.make_pair(n, n, seed=7, shear=4.0 / n)
 for inner, outer in ((30, 1), (30, 4), (2, 15)):
     s = N.Solver(N.default_params(lambda_=0.15, nscales=1, warps=1, epsilon=0.0, inner_iterations=inner, outer_iterations=outer))
+    s.set_timing(True)
     for rep in range(2):
         s.calc(I0, I1)
     st = s.stats

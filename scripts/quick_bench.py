@@ -15,6 +15,7 @@ def run(h, w, nscales, reps=2):
     s = N.Solver(N.default_params(lambda_=0.15, nscales=nscales, warps=int(os.environ.get('WARPS', 5)), inner_iterations=30, outer_iterations=10))
     if os.environ.get("FUSED_MIN_PX"):
         s.set_option("fused_min_px", float(os.environ["FUSED_MIN_PX"]))
+    s.set_timing(True)
     for r in range(reps):
         t = time.time(); u, v = s.calc(I0, I1); dt = time.time() - t
         st = s.stats

@@ -10,6 +10,7 @@ for (h, w) in ((100, 4096), (200, 4096), (100, 8192)):
     s = N.Solver(N.default_params())          # reference-wrapper defaults
     if os.environ.get("FUSED_MIN_PX"):
         s.set_option("fused_min_px", float(os.environ["FUSED_MIN_PX"]))
+    s.set_timing(True)
     for rep in range(3):
         t = time.time(); u, v = s.calc(I0, I1); dt = time.time() - t
     st = s.stats

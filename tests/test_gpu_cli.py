@@ -164,3 +164,36 @@ def test_general_scale_and_prefetch(gpu, orc, tmp_path):
         base = str(tmp_path / ("p%d_0.30" % a))
         assert np.array_equal(read_tiff_f32(base + "_x.tiff"), ou)
         assert np.array_equal(read_tiff_f32(base + "_y.tiff"), ov)
+
+
+def test_sharded_random_points_cover_every_pair(gpu, tmp_path):
+    """--shard R/W (one process per GPU): every rank writes its own batch files, so the union of the
+    outputs holds every pair exactly once; a pair with a bad roi is logged and skipped, the job goes
+    on and its pending matches are still flushed; "matches_file" collects every batch of a process."""
+    exe = build_cli()
+    sl = synth.make_stack(5, 64, 96, seed=9)
+    names = []
+    for k, a in enumerate(sl):
+        p = str(tmp_path / ("h%d.png" % k))
+        write_png(p, a)
+        names.append(p)
+    images = [{"p": names[k], "q": names[k + 1], "pId": "h%d" % k, "qId": "h%d" % (k + 1),
+               "pGroupId": "%d.0" % k, "qGroupId": "%d.0" % (k + 1)} for k in range(5)]
+    images[3]["rois"] = {"custom": [0, 0, 4000, 10]}            # outside the frame: skipped, not fatal
+    job = {"debug": True, "output_type": "random_points", "scale": 1.0, "lambda": 0.15, "nscales": 2, "npoints": 3,
+           "batch_size": 0, "output_dir": str(tmp_path), "images": images}
+    jf = str(tmp_path / "job.json")
+    json.dump(job, open(jf, "w"))
+    for r in range(2):
+        subprocess.check_call([exe, "--shard", "%d/2" % r, jf], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    seen = []
+    files = sorted(f for f in os.listdir(str(tmp_path)) if f.startswith("point_matches_"))
+    assert files and all("_r0of2_" in f or "_r1of2_" in f for f in files)
+    for f in files:
+        seen += [g["pId"] for g in json.load(open(str(tmp_path / f)))]
+    assert sorted(seen) == ["h0", "h1", "h2", "h4"]             # each once; h3 skipped
+    # matches_file: all batches of the process in one array
+    job["matches_file"] = str(tmp_path / "all.json")
+    json.dump(job, open(jf, "w"))
+    subprocess.check_call([exe, jf], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    assert [g["pId"] for g in json.load(open(job["matches_file"]))] == ["h0", "h1", "h2", "h4"]

@@ -109,6 +109,23 @@ def test_iterate_fused2(gpu, orc, h, w, n):
     np.testing.assert_allclose(got[6], werr, rtol=1e-12)
 
 
+@pytest.mark.parametrize("h,w", SIZES[:2] + [(200, 700)])
+@pytest.mark.parametrize("n", [1, 5, 8])
+def test_iterate_outer(gpu, orc, h, w, n):
+    """k_outer, the kernel the solver ships: n iterations in one cooperative launch (two-iteration
+    passes + a single pass for odd n): same states, same per-iteration errors"""
+    rng = np.random.default_rng(6)
+    consts, state = make_iter_inputs(rng, h, w)
+    l_t, theta, taut = np.float32(0.15 * 0.3), np.float32(0.3), np.float32(0.25 / 0.3)
+    want = [s.copy() for s in state]
+    werr = [orc.iterate(*consts, *want, l_t, theta, taut) for _ in range(n)]
+    got = gpu.k_iterate(*consts, *state, l_t, theta, taut, n=n, fused="outer")
+    names = ["u1", "u2", "p11", "p12", "p21", "p22"]
+    for k in range(6):
+        assert np.array_equal(got[k], want[k]), names[k]
+    np.testing.assert_allclose(got[6], werr, rtol=1e-12)
+
+
 def test_prescale_u8(gpu, orc):
     """tvl1_prescale_u8: the loader's 8-bit cv::resize on the device -- cv2-made golden vectors and,
     at a realistic size, the oracle."""

@@ -216,3 +216,31 @@ def test_whole_pair_vs_cv2_composition_params(orc, cv2_plain, h, w, seed, kw):
     assert lev == rit.shape[0]
     assert np.array_equal(it[:lev], rit)
     assert np.array_equal(u, ru) and np.array_equal(v, rv)
+
+
+def test_oracle_vs_opencv_dualtvl1(orc):
+    """The oracle's COMPOSITION against OpenCV's own DualTVL1 class: from the committed golden file if a
+    maintainer has generated it (tests/golden/make_opencv_dualtvl1_golden.py), else from the live class
+    if this cv2 has one; skipped -- parity of the composition stays UNPINNED -- while neither exists
+    (the case in this image: opencv-python-headless has no optflow module)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("mk_cv_golden", os.path.join(GOLD, "make_opencv_dualtvl1_golden.py"))
+    mk = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mk)
+    stored = np.load(mk.OUT) if os.path.exists(mk.OUT) else None
+    factory = mk.opencv_factory()
+    if stored is None and factory is None:
+        pytest.skip("no OpenCV DualTVL1 available and no opencv_dualtvl1.npz: composition parity unpinned")
+    for k, I0, I1, prm in mk.cases():
+        if stored is not None:
+            assert np.array_equal(stored["I0_%d" % k], I0) and np.array_equal(stored["I1_%d" % k], I1)
+            cu, cv = stored["u_%d" % k], stored["v_%d" % k]
+        else:
+            cu, cv = mk.opencv_solve(factory, I0, I1, prm)
+        kw = {"tau": prm["tau"], "lambda": prm["lambda_"], "theta": prm["theta"], "nscales": prm["nscales"],
+              "warps": prm["warps"], "epsilon": prm["epsilon"], "inner_iterations": prm["innerIterations"],
+              "outer_iterations": prm["outerIterations"], "scale_step": prm["scaleStep"],
+              "median_filtering": prm["medianFiltering"], "error_sum_mode": 1}   # 1: OpenCV's literal serial fp32 sum
+        ou, ov, _, _ = orc.tvl1_calc(I0, I1, **kw)
+        epe = np.hypot(ou - cu, ov - cv)
+        assert epe.mean() <= 0.01 and epe.max() <= 0.1, (k, float(epe.mean()), float(epe.max()))   # north_star bounds
