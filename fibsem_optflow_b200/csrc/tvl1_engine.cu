@@ -571,7 +571,7 @@ static int calc_device(tvl1_handle* H, const uint8_t* f0, size_t pitch0, const u
         ia.u1[0] = lv.u1; ia.u1[1] = H->u1x; ia.u2[0] = lv.u2; ia.u2[1] = H->u2x;
         for (int k = 0; k < 2; k++) { ia.p11[k] = H->p[0][k]; ia.p12[k] = H->p[1][k]; ia.p21[k] = H->p[2][k]; ia.p22[k] = H->p[3][k]; }
         ia.w = lv.w; ia.h = lv.h; ia.pitch = lv.pitch;
-        ia.l_t = l_t; ia.theta = theta; ia.taut = taut; ia.scaled_eps = scaled_eps;
+        ia.l_t = l_t; ia.theta = theta; ia.taut = taut; ia.scaled_eps = scaled_eps; ia.one = 1.0f;
         ia.level = s; ia.ctrl = H->d_ctrl; ia.partials = H->d_partials; ia.errlog = nullptr;
         ia.mode = 0; ia.inner_max = H->inner;
         const bool fused = (long long)lv.w * lv.h >= H->fused_min_px && H->inner >= 2;
@@ -1094,7 +1094,7 @@ static int k_iterate_impl(int fused, const float* d_I1wx, const float* d_I1wy, c
     a.u1[0] = d_u1; a.u1[1] = tw[0]; a.u2[0] = d_u2; a.u2[1] = tw[1];
     a.p11[0] = d_p11; a.p11[1] = tw[2]; a.p12[0] = d_p12; a.p12[1] = tw[3];
     a.p21[0] = d_p21; a.p21[1] = tw[4]; a.p22[0] = d_p22; a.p22[1] = tw[5];
-    a.w = w; a.h = h; a.pitch = pitch; a.l_t = l_t; a.theta = theta; a.taut = taut;
+    a.w = w; a.h = h; a.pitch = pitch; a.l_t = l_t; a.theta = theta; a.taut = taut; a.one = 1.0f;
     a.scaled_eps = -1.f;   // never stops
     a.level = 0; a.slot = 0; a.mode = 0; a.inner_max = 1 << 30;
     a.ctrl = (Ctrl*)(tmp + ctrl_off);
