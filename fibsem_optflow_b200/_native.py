@@ -72,10 +72,11 @@ EXPORTS = [
     "tvl1_version", "tvl1_last_error", "tvl1_default_params", "tvl1_create", "tvl1_destroy",
     "tvl1_set_params", "tvl1_set_option", "tvl1_set_timing", "tvl1_calc_u8", "tvl1_calc_u8_host",
     "tvl1_prescaled_size", "tvl1_prescale_u8", "tvl1_prescale_u8_host",
-    "tvl1_mask_flow_u8", "tvl1_sample_matches", "tvl1_sample_matches_skip", "tvl1_stack_run", "tvl1_k_convert_u8", "tvl1_k_resize",
+    "tvl1_mask_flow_u8", "tvl1_finish_flow_u8", "tvl1_sample_matches", "tvl1_sample_matches_skip", "tvl1_stack_run", "tvl1_k_convert_u8", "tvl1_k_resize",
     "tvl1_k_centered_gradient", "tvl1_k_warp", "tvl1_k_iterate", "tvl1_k_iterate_fused2", "tvl1_k_outer", "tvl1_k_median5", "tvl1_k_last_ms",
     "tvl1_pyramid_sizes", "tvl1_glibc_rand", "tvl1_selftest_arith", "tvl1_dev_count", "tvl1_dev_alloc", "tvl1_dev_free",
-    "tvl1_dev_memset", "tvl1_dev_h2d", "tvl1_dev_d2h", "tvl1_dev_sync",
+    "tvl1_dev_memset", "tvl1_dev_h2d", "tvl1_dev_d2h", "tvl1_dev_sync", "tvl1_set_device", "tvl1_stream_create",
+    "tvl1_stream_destroy", "tvl1_stream_sync", "tvl1_stream_query", "tvl1_stream_wait", "tvl1_dev_h2d_async", "tvl1_dev_d2h_async",
     "tvl1_host_alloc_pinned", "tvl1_host_free_pinned",
 ]
 
@@ -116,6 +117,7 @@ def lib():
     L.tvl1_calc_u8_host.argtypes = [_vp, _vp, _sz, _vp, _sz, C.c_int, C.c_int, _vp, _vp, _sz,
                                     C.POINTER(Stats)]
     L.tvl1_mask_flow_u8.argtypes = [_vp, _vp, _sz, C.c_int, C.c_int, _vp, _vp, _sz, _vp]
+    L.tvl1_finish_flow_u8.argtypes = [_vp, _vp, _sz, C.c_int, C.c_int, _vp, _vp, _sz, C.c_int, _vp]
     L.tvl1_sample_matches.argtypes = [_vp, _vp, _sz, _vp, _sz, _vp, _vp, _sz, C.c_int, C.c_int,
                                       C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int,
                                       C.c_longlong, _vp, _vp, _vp, _vp, _vp, _vp,
@@ -144,6 +146,13 @@ def lib():
     L.tvl1_dev_h2d.argtypes = [_vp, _vp, _sz]
     L.tvl1_dev_d2h.argtypes = [_vp, _vp, _sz]
     L.tvl1_dev_sync.argtypes = [C.c_int]
+    L.tvl1_set_device.argtypes = [C.c_int]
+    L.tvl1_stream_create.argtypes = [C.c_int, C.POINTER(_vp)]
+    for _n in ("tvl1_stream_destroy", "tvl1_stream_sync", "tvl1_stream_query"):
+        getattr(L, _n).argtypes = [_vp]
+    L.tvl1_stream_wait.argtypes = [_vp, _vp]
+    L.tvl1_dev_h2d_async.argtypes = [_vp, _vp, _sz, _vp]
+    L.tvl1_dev_d2h_async.argtypes = [_vp, _vp, _sz, _vp]
     L.tvl1_host_alloc_pinned.argtypes = [_sz, C.POINTER(_vp)]
     L.tvl1_host_free_pinned.argtypes = [_vp]
     _lib = L
@@ -335,6 +344,10 @@ class Solver:
 
     def mask_flow_device(self, d_f1, pitch1, w, h, d_u, d_v, pitch_out, stream=None):
         check(lib().tvl1_mask_flow_u8(self.handle, d_f1, pitch1, w, h, d_u, d_v, pitch_out, stream))
+
+    def finish_flow_device(self, d_f1, pitch1, w, h, d_u, d_v, pitch_out, add_grid, stream=None):
+        """output_type "map": + coordinate grid; then flow = 0 where frame1 <= 1 (src/optflow.cpp:445-473)"""
+        check(lib().tvl1_finish_flow_u8(self.handle, d_f1, pitch1, w, h, d_u, d_v, pitch_out, int(bool(add_grid)), stream))
 
     def sample_matches_device(self, d_f0, pitch0, d_f1, pitch1, d_u, d_v, pitch_flow, w, h,
                               roi0=(0, 0), roi1=(0, 0), scale=0.5, npoints=25, seed=-1,

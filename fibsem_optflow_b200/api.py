@@ -113,18 +113,12 @@ def solve_wrapper(frame0, frame1, im_args, args, roi_vec=((0, 0), (0, 0)), devic
     bv = N.DevBuf(w * h * 4, device)
     try:
         s.calc_device(b0.ptr, w, b1.ptr, w, w, h, bu.ptr, bv.ptr, w * 4)
-        s.mask_flow_device(b1.ptr, w, w, h, bu.ptr, bv.ptr, w * 4)
+        # coordinate grid ("map") added BEFORE the mask in the reference (:445-466 then :471-473), so
+        # masked pixels are 0, not their coordinate; both on the device, in one pass
+        s.finish_flow_device(b1.ptr, w, w, h, bu.ptr, bv.ptr, w * 4, output_type == "map")
         flow_x = bu.download((h, w), np.float32)
         flow_y = bv.download((h, w), np.float32)
-        if output_type == "map":
-            # coordinate grid added BEFORE the mask in the reference (:445-466 then :471-473),
-            # so masked pixels are 0, not their coordinate
-            m = frame1 <= 1
-            flow_x = np.where(m, np.float32(0), flow_x + np.arange(w, dtype=np.float32)[None, :])
-            flow_y = np.where(m, np.float32(0), flow_y + np.arange(h, dtype=np.float32)[:, None])
-            flow_x = flow_x.astype(np.float32)
-            flow_y = flow_y.astype(np.float32)
-        elif output_type == "random_points":
+        if output_type == "random_points":
             debug = bool(args.get("debug", False))
             if seed is None:
                 import time

@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <vector>
 
 #include "tvl1_kernels.cuh"
@@ -871,16 +872,29 @@ int tvl1_calc_u8_host(tvl1_handle* H, const uint8_t* h_frame0, size_t pitch0, co
     return TVL1_OK;
 }
 
+static int launch_mask_flow(const uint8_t* f1, size_t pitch1, int w, int h, float* u, float* v, size_t pitch_f, int add_grid,
+                            cudaStream_t st)
+{
+    dim3 b(32, 8);
+    dim3 g(cdiv(cdiv(w, 4), 32), cdiv(h, 8));
+    k_mask_flow<<<g, b, 0, st>>>(f1, pitch1, w, h, u, v, pitch_f, add_grid);
+    CK(cudaGetLastError());
+    return TVL1_OK;
+}
+
+int tvl1_finish_flow_u8(tvl1_handle* H, const uint8_t* d_frame1, size_t pitch1, int width, int height,
+                        float* d_u, float* d_v, size_t pitch_out, int add_grid, void* stream)
+{
+    if (!H) return fail(TVL1_ERR_INVALID, "handle is null");
+    if (!d_frame1 || !d_u || !d_v || width <= 0 || height <= 0 || pitch_out % 4) return fail(TVL1_ERR_INVALID, "bad argument");
+    CK(cudaSetDevice(H->device));
+    return launch_mask_flow(d_frame1, pitch1, width, height, d_u, d_v, pitch_out / 4, add_grid != 0, (cudaStream_t)stream);
+}
+
 int tvl1_mask_flow_u8(tvl1_handle* H, const uint8_t* d_frame1, size_t pitch1, int width, int height,
                       float* d_u, float* d_v, size_t pitch_out, void* stream)
 {
-    if (!H) return fail(TVL1_ERR_INVALID, "handle is null");
-    if (!d_frame1 || !d_u || !d_v || width <= 0 || height <= 0) return fail(TVL1_ERR_INVALID, "bad argument");
-    CK(cudaSetDevice(H->device));
-    dim3 b(32, 8);
-    k_mask_flow<<<grid2d(width, height, b), b, 0, (cudaStream_t)stream>>>(d_frame1, pitch1, width, height, d_u, d_v, pitch_out / 4);
-    CK(cudaGetLastError());
-    return TVL1_OK;
+    return tvl1_finish_flow_u8(H, d_frame1, pitch1, width, height, d_u, d_v, pitch_out, 0, stream);
 }
 
 // ---- stack of adjacent slices
@@ -977,11 +991,7 @@ int tvl1_stack_run(tvl1_handle* H, const tvl1_stack_io* io, float* ms_total)
         rc = calc_device(H, H->st_slice[s0], p8, H->st_slice[s1], p8, w, h, du, dv, (size_t)w * 4, cs,
                          io->stats ? &io->stats[k] : nullptr);
         if (rc) return rc;
-        if (io->apply_mask) {
-            dim3 b(32, 8);
-            k_mask_flow<<<grid2d(w, h, b), b, 0, cs>>>(H->st_slice[s1], p8, w, h, du, dv, (size_t)w);
-            CK(cudaGetLastError());
-        }
+        if (io->apply_mask && (rc = launch_mask_flow(H->st_slice[s1], p8, w, h, du, dv, (size_t)w, 0, cs))) return rc;
         if (io->npoints >= 0) {
             long long used = 0;
             const size_t o = (size_t)k * cap;
@@ -1224,18 +1234,27 @@ int tvl1_prescale_u8_host(int device, const uint8_t* src, size_t spitch, int w, 
     int rc = tvl1_prescaled_size(w, h, scale, &dw, &dh);
     if (rc) return rc;
     if (!src || !dst || spitch < (size_t)w || dpitch < (size_t)dw) return fail(TVL1_ERR_INVALID, "bad buffer or pitch");
+    if (device < 0 || device >= 64) return fail(TVL1_ERR_INVALID, "device out of range");
     CK(cudaSetDevice(device));
-    uint8_t *ds = nullptr, *dd = nullptr;
-    CK(cudaMalloc(&ds, (size_t)w * h));
-    if (cudaMalloc(&dd, (size_t)dw * dh) != cudaSuccess) { cudaFree(ds); return fail(TVL1_ERR_CUDA, "cudaMalloc failed"); }
-    rc = TVL1_OK;
-    if (cudaMemcpy2D(ds, w, src, spitch, w, h, cudaMemcpyHostToDevice) != cudaSuccess) rc = fail(TVL1_ERR_CUDA, "upload failed");
-    if (!rc) rc = tvl1_prescale_u8(ds, w, w, h, scale, dd, dw, nullptr);
-    if (!rc && cudaMemcpy2D(dst, dpitch, dd, dw, dw, dh, cudaMemcpyDeviceToHost) != cudaSuccess)
-        rc = fail(TVL1_ERR_CUDA, "download failed: %s", cudaGetErrorString(cudaGetLastError()));
-    cudaFree(ds);
-    cudaFree(dd);
-    return rc;
+    // grow-only scratch per device (this entry point has no handle to keep it in): no cudaMalloc per call
+    struct Scratch { uint8_t* p = nullptr; size_t cap = 0; };
+    static Scratch scratch[64];
+    static std::mutex mtx;
+    std::lock_guard<std::mutex> lock(mtx);
+    Scratch& S = scratch[device];
+    const size_t raw = ((size_t)w * h + 255) / 256 * 256, need = raw + (size_t)dw * dh;
+    if (S.cap < need) {
+        if (S.p) cudaFree(S.p);
+        S.p = nullptr; S.cap = 0;
+        CK(cudaMalloc(&S.p, need));
+        S.cap = need;
+    }
+    uint8_t *ds = S.p, *dd = S.p + raw;
+    if (cudaMemcpy2D(ds, w, src, spitch, w, h, cudaMemcpyHostToDevice) != cudaSuccess) return fail(TVL1_ERR_CUDA, "upload failed");
+    if ((rc = tvl1_prescale_u8(ds, w, w, h, scale, dd, dw, nullptr))) return rc;
+    if (cudaMemcpy2D(dst, dpitch, dd, dw, dw, dh, cudaMemcpyDeviceToHost) != cudaSuccess)
+        return fail(TVL1_ERR_CUDA, "download failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return TVL1_OK;
 }
 
 // ---- device-memory helpers
@@ -1266,6 +1285,46 @@ int tvl1_dev_memset(void* d, int v, size_t bytes) { CK(cudaMemset(d, v, bytes));
 int tvl1_dev_h2d(void* d, const void* h, size_t bytes) { CK(cudaMemcpy(d, h, bytes, cudaMemcpyHostToDevice)); return TVL1_OK; }
 int tvl1_dev_d2h(void* h, const void* d, size_t bytes) { CK(cudaMemcpy(h, d, bytes, cudaMemcpyDeviceToHost)); return TVL1_OK; }
 int tvl1_dev_sync(int device) { CK(cudaSetDevice(device)); CK(cudaDeviceSynchronize()); return TVL1_OK; }
+int tvl1_set_device(int device) { CK(cudaSetDevice(device)); return TVL1_OK; }
+int tvl1_stream_create(int device, void** out)
+{
+    if (!out) return fail(TVL1_ERR_INVALID, "out is null");
+    CK(cudaSetDevice(device));
+    cudaStream_t s;
+    CK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    *out = (void*)s;
+    return TVL1_OK;
+}
+int tvl1_stream_destroy(void* stream) { CK(cudaStreamDestroy((cudaStream_t)stream)); return TVL1_OK; }
+int tvl1_stream_sync(void* stream) { CK(cudaStreamSynchronize((cudaStream_t)stream)); return TVL1_OK; }
+// everything enqueued on `signaller` so far must finish before work enqueued on `waiter` after this call
+int tvl1_stream_wait(void* waiter, void* signaller)
+{
+    cudaEvent_t e;
+    CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    cudaError_t r = cudaEventRecord(e, (cudaStream_t)signaller);
+    if (r == cudaSuccess) r = cudaStreamWaitEvent((cudaStream_t)waiter, e, 0);
+    cudaEventDestroy(e);   // released once the recorded work has completed
+    if (r != cudaSuccess) return fail(TVL1_ERR_CUDA, "stream wait: %s", cudaGetErrorString(r));
+    return TVL1_OK;
+}
+int tvl1_stream_query(void* stream)
+{
+    const cudaError_t r = cudaStreamQuery((cudaStream_t)stream);
+    if (r == cudaSuccess) return 1;
+    if (r == cudaErrorNotReady) { cudaGetLastError(); return 0; }
+    return fail(TVL1_ERR_CUDA, "stream query: %s", cudaGetErrorString(r));
+}
+int tvl1_dev_h2d_async(void* d, const void* h, size_t bytes, void* stream)
+{
+    CK(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    return TVL1_OK;
+}
+int tvl1_dev_d2h_async(void* h, const void* d, size_t bytes, void* stream)
+{
+    CK(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return TVL1_OK;
+}
 int tvl1_host_alloc_pinned(size_t bytes, void** out)
 {
     if (!out) return fail(TVL1_ERR_INVALID, "out is null");

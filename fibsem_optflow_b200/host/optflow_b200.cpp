@@ -16,12 +16,17 @@
 //     without the alignment the reference would force (:366);
 //   * match batches are written to <output_dir>/point_matches_<n>.json with exactly the payload
 //     upload_points would PUT to the Render service (:620-634) -- there is no network here;
-// N2: every decoded frame is prescaled by `scale` on the device (tvl1_prescale_u8_host: the 8-bit
-// cv::resize of :111,124, bit for bit, any factor), and the NEXT pair's frames are decoded on a host
-// thread while the current pair is solved.
+// N2, the I/O path: frames are decoded on host threads into PINNED buffers `prefetch` pairs ahead; a
+// decoded frame goes up once on a copy stream, is prescaled by `scale` there (tvl1_prescale_u8: the
+// 8-bit cv::resize of :111,124, bit for bit, any factor) and stays on the device in one of three frame
+// slots, so the slice two adjacent pairs share is neither decoded nor uploaded twice (:97-103) and the
+// next pair's new frame arrives while the current pair is solved.  The coordinate grid of "map" and the
+// frame1 <= 1 mask are applied on the device (tvl1_finish_flow_u8); flow planes come down into pinned
+// buffers and are written to TIFF on a host thread while the next pair is solved.
 // All arithmetic runs in libtvl1_b200.so; this file only moves bytes and JSON.
 #include <zlib.h>
 
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -30,6 +35,7 @@
 #include <future>
 #include <iostream>
 #include <map>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -44,9 +50,53 @@ namespace {
 
 struct Rect { int x, y, w, h; };
 
-struct DeviceFrame {
+struct DeviceBuf {
     void* ptr = nullptr;
     size_t bytes = 0;
+};
+
+// pinned host buffers, recycled: taken by the decode threads and the flow downloads, returned when the
+// copy / the TIFF writer is done with them
+struct PinnedPool {
+    int device = 0;
+    std::mutex m;
+    std::vector<std::pair<void*, size_t>> free_;
+    void* get(size_t bytes, size_t* cap)
+    {
+        {
+            std::lock_guard<std::mutex> l(m);
+            for (size_t k = 0; k < free_.size(); k++)
+                if (free_[k].second >= bytes) {
+                    void* p = free_[k].first;
+                    *cap = free_[k].second;
+                    free_.erase(free_.begin() + (long)k);
+                    return p;
+                }
+        }
+        void* p = nullptr;
+        tvl1_set_device(device);   // the calling thread may be a decode thread: same device, same context
+        if (tvl1_host_alloc_pinned(bytes, &p) < 0) return nullptr;
+        *cap = bytes;
+        return p;
+    }
+    void put(void* p, size_t cap)
+    {
+        std::lock_guard<std::mutex> l(m);
+        free_.emplace_back(p, cap);
+    }
+    ~PinnedPool()
+    {
+        for (auto& f : free_) tvl1_host_free_pinned(f.first);
+    }
+};
+
+// a prescaled frame resident on the device
+struct FrameSlot {
+    std::string name;
+    float scale = -1.f;
+    DeviceBuf buf;
+    int w = 0, h = 0;
+    long long last_use = -1;   // pair index
 };
 
 struct Driver {
@@ -55,7 +105,12 @@ struct Driver {
     tvl1_handle* solver = nullptr;
     tvl1_params cur{};
     bool have_params = false;
-    DeviceFrame d0, d1, du, dv;
+    void *s_solve = nullptr, *s_copy = nullptr;   // streams
+    FrameSlot slot[3];
+    DeviceBuf raw, du, dv;
+    PinnedPool pool;
+    std::vector<std::pair<void*, size_t>> in_copy;   // pinned buffers the copy stream may still read
+    std::vector<std::future<bool>> writers;          // TIFF writers in flight
     long long rand_skip = 0;   // debug mode: one rand() stream for the whole process
     int uploads = 0;
     int shard = 0, nshards = 1, skipped = 0;
@@ -63,8 +118,12 @@ struct Driver {
 
     ~Driver()
     {
+        for (auto& w : writers) w.get();
+        if (s_copy) { tvl1_stream_sync(s_copy); tvl1_stream_destroy(s_copy); }
+        if (s_solve) { tvl1_stream_sync(s_solve); tvl1_stream_destroy(s_solve); }
+        for (auto& b : in_copy) pool.put(b.first, b.second);
         if (solver) tvl1_destroy(solver);
-        for (DeviceFrame* f : {&d0, &d1, &du, &dv})
+        for (DeviceBuf* f : {&slot[0].buf, &slot[1].buf, &slot[2].buf, &raw, &du, &dv})
             if (f->ptr) tvl1_dev_free(device, f->ptr);
     }
 };
@@ -104,7 +163,7 @@ std::string slurp(const std::string& path)
     return s;
 }
 
-void reserve(Driver& D, DeviceFrame& f, size_t bytes)
+void reserve(Driver& D, DeviceBuf& f, size_t bytes)
 {
     if (f.bytes >= bytes) return;
     if (f.ptr) tvl1_dev_free(D.device, f.ptr);
@@ -182,8 +241,8 @@ void check_roi(const Rect& r, int w, int h, const char* which)
         pair_fail(std::string("roi outside the frame (") + which + ")");
 }
 
-// solve_wrapper (src/optflow.cpp:395-497), features == false
-void solve_wrapper(Driver& D, const imio::Gray8& f0, const imio::Gray8& f1, const Rect& r0, const Rect& r1,
+// solve_wrapper (src/optflow.cpp:395-497), features == false.  f0 / f1: the pair's frames on the device.
+void solve_wrapper(Driver& D, const FrameSlot& f0, const FrameSlot& f1, const Rect& r0, const Rect& r1,
                    Value& im, const Value& args)
 {
     if (r0.w != r1.w || r0.h != r1.h) pair_fail("the two rois of a pair must have the same size");
@@ -191,15 +250,16 @@ void solve_wrapper(Driver& D, const imio::Gray8& f0, const imio::Gray8& f1, cons
     ensure_solver(D, tv_params(im, args));
     reserve(D, D.du, (size_t)w * h * 4);
     reserve(D, D.dv, (size_t)w * h * 4);
-    const uint8_t* p0 = (const uint8_t*)D.d0.ptr + (size_t)r0.y * f0.w + r0.x;   // ROI views: pointer + pitch
-    const uint8_t* p1 = (const uint8_t*)D.d1.ptr + (size_t)r1.y * f1.w + r1.x;
-    ck(tvl1_calc_u8(D.solver, p0, (size_t)f0.w, p1, (size_t)f1.w, w, h, (float*)D.du.ptr, (float*)D.dv.ptr,
-                    (size_t)w * 4, nullptr, nullptr), "tvl1_calc_u8");
+    const uint8_t* p0 = (const uint8_t*)f0.buf.ptr + (size_t)r0.y * f0.w + r0.x;   // ROI views: pointer + pitch
+    const uint8_t* p1 = (const uint8_t*)f1.buf.ptr + (size_t)r1.y * f1.w + r1.x;
+    float *du = (float*)D.du.ptr, *dv = (float*)D.dv.ptr;
+    ck(tvl1_calc_u8(D.solver, p0, (size_t)f0.w, p1, (size_t)f1.w, w, h, du, dv, (size_t)w * 4, D.s_solve, nullptr), "tvl1_calc_u8");
 
     const std::string output_type = pick(im, args, "output_type", Value("map")).asString();
+    // the coordinate grid of "map" (:445-466) and the frame1 <= 1 mask (:471-473), on the device
+    ck(tvl1_finish_flow_u8(D.solver, p1, (size_t)f1.w, w, h, du, dv, (size_t)w * 4, output_type == "map", D.s_solve),
+       "tvl1_finish_flow_u8");
     if (output_type == "random_points") {
-        ck(tvl1_mask_flow_u8(D.solver, p1, (size_t)f1.w, w, h, (float*)D.du.ptr, (float*)D.dv.ptr, (size_t)w * 4, nullptr),
-           "tvl1_mask_flow_u8");
         const bool debug = args.get("debug", Value(false)).asBool();
         const float scale = pick(im, args, "scale", Value(0.5)).asFloat();
         const int npoints = (int)pick(im, args, "npoints", Value(25)).asInt();
@@ -209,10 +269,9 @@ void solve_wrapper(Driver& D, const imio::Gray8& f0, const imio::Gray8& f1, cons
         long long used = 0;
         // srand(time(0)) unless debug (:532-535); debug keeps drawing from one unseeded stream
         const long long seed = debug ? -1 : (long long)std::time(nullptr);
-        ck(tvl1_sample_matches_skip(D.solver, p0, (size_t)f0.w, p1, (size_t)f1.w, (float*)D.du.ptr, (float*)D.dv.ptr,
-                                    (size_t)w * 4, w, h, r0.x, r0.y, r1.x, r1.y, scale, npoints, seed,
-                                    debug ? D.rand_skip : 0, px.data(), py.data(), qx.data(), qy.data(), wt.data(),
-                                    nullptr, &n, &used, nullptr), "tvl1_sample_matches");
+        ck(tvl1_sample_matches_skip(D.solver, p0, (size_t)f0.w, p1, (size_t)f1.w, du, dv, (size_t)w * 4, w, h, r0.x, r0.y,
+                                    r1.x, r1.y, scale, npoints, seed, debug ? D.rand_skip : 0, px.data(), py.data(),
+                                    qx.data(), qy.data(), wt.data(), nullptr, &n, &used, D.s_solve), "tvl1_sample_matches");
         if (debug) D.rand_skip += used;
         Value& pm = im["point_matches"];
         if (!pm.isMember("p")) {
@@ -227,22 +286,29 @@ void solve_wrapper(Driver& D, const imio::Gray8& f0, const imio::Gray8& f1, cons
         }
         return;
     }
-    // "map" | "flow": planes to the host, coordinate grid (map), mask, float TIFFs
-    std::vector<float> fx((size_t)w * h), fy((size_t)w * h);
-    ck(tvl1_dev_d2h(fx.data(), D.du.ptr, fx.size() * 4), "download");
-    ck(tvl1_dev_d2h(fy.data(), D.dv.ptr, fy.size() * 4), "download");
-    const bool map = output_type == "map";
-    for (int y = 0; y < h; y++) {
-        const uint8_t* m = &f1.px[(size_t)(r1.y + y) * f1.w + r1.x];
-        for (int x = 0; x < w; x++) {
-            const size_t i = (size_t)y * w + x;
-            if (map) { fx[i] = fx[i] + (float)x; fy[i] = fy[i] + (float)y; }   // :451-465
-            if (m[x] <= 1) { fx[i] = 0.f; fy[i] = 0.f; }                       // :471-473
-        }
+    // "map" | "flow": planes into pinned host buffers, float TIFFs written by a host thread while the
+    // next pair is solved (at most two writers in flight)
+    const size_t nb = (size_t)w * h * 4;
+    size_t capx = 0, capy = 0;
+    float* hx = (float*)D.pool.get(nb, &capx);
+    float* hy = (float*)D.pool.get(nb, &capy);
+    if (!hx || !hy) die("pinned host allocation failed");
+    ck(tvl1_dev_d2h_async(hx, du, nb, D.s_solve), "download");
+    ck(tvl1_dev_d2h_async(hy, dv, nb, D.s_solve), "download");
+    ck(tvl1_stream_sync(D.s_solve), "download");
+    while (D.writers.size() >= 2) {
+        if (!D.writers.front().get()) die("cannot write a flow TIFF");
+        D.writers.erase(D.writers.begin());
     }
     const std::string base = im.at("output").asString() + im.at("output_suffix").asString();
-    if (!imio::write_tiff_f32(base + "_x.tiff", fx.data(), w, h) || !imio::write_tiff_f32(base + "_y.tiff", fy.data(), w, h))
-        pair_fail("cannot write " + base + "_{x,y}.tiff");
+    PinnedPool* pool = &D.pool;
+    D.writers.push_back(std::async(std::launch::async, [=]() {
+        const bool ok = imio::write_tiff_f32(base + "_x.tiff", hx, w, h) && imio::write_tiff_f32(base + "_y.tiff", hy, w, h);
+        if (!ok) std::cerr << "optflow_b200: cannot write " << base << "_{x,y}.tiff\n";
+        pool->put(hx, capx);
+        pool->put(hy, capy);
+        return ok;
+    }));
 }
 
 // move_pm (src/optflow.cpp:574-593)
@@ -298,35 +364,57 @@ void upload_points(Driver& D, Value& args)
     }
 }
 
-// decode only (host thread safe: touches no CUDA state)
-struct Decoded { bool ok = false; std::string err; imio::Gray8 img; };
-Decoded decode_frame(const std::string& path)
+// cv::imread(..., IMREAD_GRAYSCALE) on a host thread, into a pinned buffer (:106, :119)
+struct Decoded { bool ok = false; std::string err; int w = 0, h = 0; uint8_t* px = nullptr; size_t cap = 0; };
+Decoded decode_frame(const std::string& path, PinnedPool* pool)
 {
     Decoded d;
-    d.ok = imio::read_gray8(path, d.img, d.err);
+    imio::Gray8 img;
+    if (!imio::read_gray8(path, img, d.err)) return d;
+    d.px = (uint8_t*)pool->get(img.px.size(), &d.cap);
+    if (!d.px) { d.err = "pinned host allocation failed"; return d; }
+    std::memcpy(d.px, img.px.data(), img.px.size());
+    d.w = img.w; d.h = img.h; d.ok = true;
     return d;
 }
 
-// cv::imread + cv::resize(frame, frame, Size(), scale, scale) of the reference (:106-111, :119-124);
-// the resize runs on the device
-bool finish_frame(int device, const std::string& path, Decoded&& d, float scale, imio::Gray8& out)
+// pinned buffers whose upload has completed go back to the pool
+void recycle_uploads(Driver& D, bool wait)
 {
-    if (!d.ok) {
-        std::cout << "Error: " << path << " (" << d.err << ")\n";
-        return false;
+    if (D.in_copy.empty()) return;
+    if (wait) ck(tvl1_stream_sync(D.s_copy), "copy stream");
+    else if (tvl1_stream_query(D.s_copy) != 1) return;
+    for (auto& b : D.in_copy) D.pool.put(b.first, b.second);
+    D.in_copy.clear();
+}
+
+// A decoded frame -> device slot, on the copy stream: upload, then cv::resize(frame, frame, Size(), scale,
+// scale) of the reference's loader (:111, :124) on the device.  Nothing here waits for the GPU.
+void stage_frame(Driver& D, FrameSlot& sl, const std::string& name, float scale, Decoded& d)
+{
+    int dw = d.w, dh = d.h;
+    if (scale != 1.f) ck(tvl1_prescaled_size(d.w, d.h, (double)scale, &dw, &dh), "prescale");
+    sl.name.clear();   // invalid until everything below has been enqueued
+    reserve(D, sl.buf, (size_t)dw * dh);
+    const size_t raw_bytes = (size_t)d.w * d.h;
+    if (scale == 1.f) {
+        ck(tvl1_dev_h2d_async(sl.buf.ptr, d.px, raw_bytes, D.s_copy), "upload");
+    } else {
+        if (D.raw.bytes < raw_bytes) {   // the copy stream may still be reading the old staging buffer
+            ck(tvl1_stream_sync(D.s_copy), "copy stream");
+            reserve(D, D.raw, raw_bytes);
+        }
+        ck(tvl1_dev_h2d_async(D.raw.ptr, d.px, raw_bytes, D.s_copy), "upload");
+        ck(tvl1_prescale_u8((const uint8_t*)D.raw.ptr, (size_t)d.w, d.w, d.h, (double)scale, (uint8_t*)sl.buf.ptr, (size_t)dw,
+                            D.s_copy), "prescale");
     }
-    if (scale == 1.f) { out = std::move(d.img); return true; }
-    int dw = 0, dh = 0;
-    ck(tvl1_prescaled_size(d.img.w, d.img.h, (double)scale, &dw, &dh), "prescale");
-    out.w = dw; out.h = dh;
-    out.px.resize((size_t)dw * dh);
-    ck(tvl1_prescale_u8_host(device, d.img.px.data(), (size_t)d.img.w, d.img.w, d.img.h, (double)scale, out.px.data(),
-                             (size_t)dw), "prescale");
-    return true;
+    D.in_copy.emplace_back(d.px, d.cap);
+    d.px = nullptr;
+    sl.name = name; sl.scale = scale; sl.w = dw; sl.h = dh;
 }
 
 // solve_rois (src/optflow.cpp:312-392)
-void solve_rois(Driver& D, const imio::Gray8& f0, const imio::Gray8& f1, const Value& rois, Value& im, Value& args)
+void solve_rois(Driver& D, const FrameSlot& f0, const FrameSlot& f1, const Value& rois, Value& im, Value& args)
 {
     // src/optflow.cpp:323-338: an explicit false at either level wins, then a true at either level
     bool want_features;
@@ -334,10 +422,7 @@ void solve_rois(Driver& D, const imio::Gray8& f0, const imio::Gray8& f1, const V
     else if (args.isMember("features") && !args.at("features").asBool()) want_features = false;
     else want_features = im.get("features", Value(false)).asBool() || args.get("features", Value(false)).asBool();
     if (want_features) pair_fail("\"features\" (ORB/SURF pre-alignment) is not part of this build");
-    reserve(D, D.d0, f0.px.size());
-    reserve(D, D.d1, f1.px.size());
-    ck(tvl1_dev_h2d(D.d0.ptr, f0.px.data(), f0.px.size()), "upload");
-    ck(tvl1_dev_h2d(D.d1.ptr, f1.px.data(), f1.px.size()), "upload");
+    ck(tvl1_stream_wait(D.s_solve, D.s_copy), "stream wait");   // both frames have arrived and are prescaled
     for (const auto& kv : *rois.o) {   // alphabetical, like Json::Value::getMemberNames()
         const std::string& key = kv.first;
         im["output_suffix"] = (key == "top" || key == "bottom") ? Value("_" + key) : Value("");
@@ -363,59 +448,105 @@ int from_file(Driver& D, Value& args, int shard, int nshards)
 {
     const Value images = args.at("images");
     if (!images.isArray()) die("\"images\" must be an array");
-    // the reference keeps the previous pair's frames so that a slice shared by adjacent pairs
-    // (q of pair i-1 == p of pair i) is not decoded twice (:97-103); same idea, two cache slots
-    struct Cached { std::string name; float scale = -1.f; imio::Gray8 img; };
-    Cached cache[2];
+    // The reference keeps the previous pair's decoded frames so that a slice shared by adjacent pairs (q
+    // of pair i-1 == p of pair i) is not read twice (:97-103).  Here the prescaled frames stay on the
+    // DEVICE, in three slots: two for the pair being solved, one for the frame the next pair brings.
     bool any_upload_since = false;
-    std::map<std::string, std::future<Decoded>> inflight;   // frames being decoded for the next pair
+    std::map<std::string, std::future<Decoded>> inflight;   // frames being decoded for the pairs ahead
+    PinnedPool* pool = &D.pool;
     auto prefetch = [&](const std::string& name) {
-        if (!inflight.count(name)) inflight.emplace(name, std::async(std::launch::async, decode_frame, name));
+        if (!inflight.count(name)) inflight.emplace(name, std::async(std::launch::async, decode_frame, name, pool));
     };
     const size_t n = images.size();
     const size_t base = n / nshards, rem = n % nshards;
     const size_t begin = shard * base + std::min<size_t>(shard, rem), end = begin + base + ((size_t)shard < rem ? 1 : 0);
     long long last_upload = (long long)begin;   // the batch counter starts where this shard starts
     D.shard = shard; D.nshards = nshards;
+    D.pool.device = D.device;
+    if (tvl1_stream_create(D.device, &D.s_solve) < 0 || tvl1_stream_create(D.device, &D.s_copy) < 0)
+        die(std::string("stream creation: ") + tvl1_last_error());
+    auto scale_of = [&](const Value& im) { return im.get("scale", args.get("scale", Value(0.5))).asFloat(); };
+    auto find_slot = [&](const std::string& name, float scale) -> FrameSlot* {
+        for (FrameSlot& sl : D.slot)
+            if (!sl.name.empty() && sl.name == name && sl.scale == scale) return &sl;
+        return nullptr;
+    };
+    // least recently used slot that neither `keep0` nor `keep1` occupies
+    auto victim = [&](const FrameSlot* keep0, const FrameSlot* keep1) -> FrameSlot* {
+        FrameSlot* v = nullptr;
+        for (FrameSlot& sl : D.slot)
+            if (&sl != keep0 && &sl != keep1 && (!v || sl.last_use < v->last_use)) v = &sl;
+        return v;
+    };
     for (size_t i = begin; i < end; i++) {
         Value im = images[i];
-        const std::string n0 = im.at("p").asString(), n1 = im.at("q").asString();
-        const float scale = im.get("scale", args.get("scale", Value(0.5))).asFloat();
+        std::string n0, n1;
+        try {
+        n0 = im.at("p").asString(); n1 = im.at("q").asString();
+        const float scale = scale_of(im);
         im["scale"] = Value((double)scale);
         std::cout << n0 << " " << n1 << "\n";
-        imio::Gray8 frame0, frame1;
-        auto fetch = [&](const std::string& name, imio::Gray8& out) -> bool {
-            for (Cached& c : cache)
-                if (c.name == name && c.scale == scale) { out = c.img; return true; }
-            Decoded d;
-            auto it = inflight.find(name);
-            if (it != inflight.end()) { d = it->second.get(); inflight.erase(it); }
-            else d = decode_frame(name);
-            return finish_frame(D.device, name, std::move(d), scale, out);
-        };
-        try {
-        const bool have = fetch(n0, frame0) && fetch(n1, frame1);
         // decode what the next pairs will need on host threads while this one is solved (decoding an
         // 8k x 8k PNG takes far longer than its solve, so the look-ahead -- not the GPU -- sets the pace
-        // of a job); a frame this pair or an earlier look-ahead already covers is not decoded twice
+        // of a job); a frame that is on the device already, or that an earlier look-ahead covers, is not
+        // decoded twice
         {
             std::string prev0 = n0, prev1 = n1;
             for (size_t j = i + 1; j < end && j <= i + (size_t)D.prefetch; j++) {
                 const Value& nx = images[j];
                 if (!nx.isMember("p") || !nx.isMember("q")) break;
                 const std::string m0 = nx.at("p").asString(), m1 = nx.at("q").asString();
-                // the two-slot frame cache will still hold the previous pair's frames when pair j is reached
-                if (m0 != prev0 && m0 != prev1) prefetch(m0);
-                if (m1 != prev0 && m1 != prev1 && m1 != m0) prefetch(m1);
+                const float sj = scale_of(nx);
+                // the frame slots will still hold the previous pair's frames when pair j is reached
+                if (m0 != prev0 && m0 != prev1 && !find_slot(m0, sj)) prefetch(m0);
+                if (m1 != prev0 && m1 != prev1 && m1 != m0 && !find_slot(m1, sj)) prefetch(m1);
                 prev0 = m0; prev1 = m1;
             }
         }
-        if (!have) continue;
-        cache[0].name = n0; cache[0].scale = scale; cache[0].img = frame0;
-        cache[1].name = n1; cache[1].scale = scale; cache[1].img = frame1;
+        recycle_uploads(D, false);
+        // this pair's frames: on the device already, or decoded (by the look-ahead, else now) and staged
+        auto fetch = [&](const std::string& name, const FrameSlot* keep) -> FrameSlot* {
+            if (FrameSlot* sl = find_slot(name, scale)) { sl->last_use = (long long)i; return sl; }
+            Decoded d;
+            auto it = inflight.find(name);
+            if (it != inflight.end()) { d = it->second.get(); inflight.erase(it); }
+            else d = decode_frame(name, pool);
+            if (!d.ok) {
+                std::cout << "Error: " << name << " (" << d.err << ")\n";   // :108-112, :120-124: log, next pair
+                return nullptr;
+            }
+            FrameSlot* sl = victim(keep, nullptr);
+            stage_frame(D, *sl, name, scale, d);
+            sl->last_use = (long long)i;
+            return sl;
+        };
+        FrameSlot* f0 = fetch(n0, find_slot(n1, scale));   // never evict the other frame of this pair
+        FrameSlot* f1 = f0 ? (n1 == n0 ? f0 : fetch(n1, f0)) : nullptr;
+        if (!f0 || !f1) continue;
+        // the next pair's new frame goes up now, into the third slot, if its decode has finished: the copy
+        // and the prescale then overlap this pair's solve
+        if (i + 1 < end) {
+            const Value& nx = images[i + 1];
+            if (nx.isMember("p") && nx.isMember("q")) {
+                const float sj = scale_of(nx);
+                for (const char* key : {"p", "q"}) {
+                    const std::string m = nx.at(key).asString();
+                    auto it = inflight.find(m);
+                    if (find_slot(m, sj) || it == inflight.end()) continue;
+                    if (it->second.wait_for(std::chrono::seconds(0)) != std::future_status::ready) continue;
+                    FrameSlot* sl = victim(f0, f1);
+                    if (sl->last_use == (long long)i + 1) continue;   // the one free slot is taken already
+                    Decoded d = it->second.get();
+                    inflight.erase(it);
+                    if (!d.ok) { std::cout << "Error: " << m << " (" << d.err << ")\n"; continue; }
+                    stage_frame(D, *sl, m, sj, d);
+                    sl->last_use = (long long)i + 1;
+                }
+            }
+        }
 
         Value rois = Value::object();
-        const int rows = std::min(frame0.h, frame1.h), cols = std::min(frame0.w, frame1.w);
+        const int rows = std::min(f0->h, f1->h), cols = std::min(f0->w, f1->w);
         if (im.isMember("rois")) get_rois(rois, im.at("rois"), rows, cols);
         else if (args.isMember("rois")) get_rois(rois, args.at("rois"), rows, cols);
         if (rois.size() == 0) {
@@ -427,7 +558,7 @@ int from_file(Driver& D, Value& args, int shard, int nshards)
         std::snprintf(buffer, sizeof(buffer), "%0.2f", scale);
         if (!im.isMember("output"))
             im["output"] = Value(args.at("output_dir").asString() + "/" + im.at("output_name").asString() + "_" + buffer);
-        solve_rois(D, frame0, frame1, rois, im, args);
+        solve_rois(D, *f0, *f1, rois, im, args);
         } catch (const std::exception& e) {   // PairError, or a missing / mistyped key of this pair
             std::cout << "Error: pair " << n0 << " " << n1 << " skipped (" << e.what() << ")\n";
             std::cerr << "optflow_b200: pair " << i << " skipped: " << e.what() << "\n";
@@ -446,7 +577,15 @@ int from_file(Driver& D, Value& args, int shard, int nshards)
         }
     }
     if (any_upload_since) upload_points(D, args);
-    return 0;
+    bool ok = true;
+    for (auto& w : D.writers) ok = w.get() && ok;
+    D.writers.clear();
+    for (auto& f : inflight) {   // look-ahead decodes nobody asked for in the end
+        Decoded d = f.second.get();
+        if (d.px) D.pool.put(d.px, d.cap);
+    }
+    recycle_uploads(D, true);
+    return ok ? 0 : 2;
 }
 
 }  // namespace

@@ -119,6 +119,14 @@ int tvl1_calc_u8_host(tvl1_handle* h, const uint8_t* h_frame0, size_t pitch0,
 int tvl1_mask_flow_u8(tvl1_handle* h, const uint8_t* d_frame1, size_t pitch1, int width,
                       int height, float* d_u, float* d_v, size_t pitch_out, void* stream);
 
+/* The post-processing of solve_wrapper in one pass (src/optflow.cpp:445-473): with add_grid != 0
+ * ("output_type": "map") the coordinate grid is added to the flow, u += x, v += y -- the reference
+ * builds that grid in a host double loop and uploads it (:451-465) --, then flow = 0 where
+ * frame1 <= 1 (:471-473).  add_grid == 0 is tvl1_mask_flow_u8. */
+int tvl1_finish_flow_u8(tvl1_handle* h, const uint8_t* d_frame1, size_t pitch1, int width,
+                        int height, float* d_u, float* d_v, size_t pitch_out, int add_grid,
+                        void* stream);
+
 /* random_points (features == false path).  mask = (frame0 > 1) | (frame1 > 1); the mask's
  * non-zero pixels in row-major order are shuffled exactly as libstdc++'s
  * std::random_shuffle driven by glibc rand() does: seed < 0 reproduces the reference's
@@ -185,7 +193,7 @@ int tvl1_stack_run(tvl1_handle* h, const tvl1_stack_io* io, float* ms_total);
 int tvl1_prescaled_size(int w, int h, double scale, int* dw, int* dh);
 int tvl1_prescale_u8(const uint8_t* d_src, size_t spitch, int w, int h, double scale,
                      uint8_t* d_dst, size_t dpitch, void* stream);
-/* host buffers: upload, prescale, download (blocking; scratch allocated per call) */
+/* host buffers: upload, prescale, download (blocking; device scratch is kept per device and only grows) */
 int tvl1_prescale_u8_host(int device, const uint8_t* src, size_t spitch, int w, int h, double scale,
                           uint8_t* dst, size_t dpitch);
 
@@ -247,6 +255,16 @@ int tvl1_dev_memset(void* d_dst, int value, size_t bytes);
 int tvl1_dev_h2d(void* d_dst, const void* h_src, size_t bytes);
 int tvl1_dev_d2h(void* h_dst, const void* d_src, size_t bytes);
 int tvl1_dev_sync(int device);
+/* streams and asynchronous copies for callers that overlap I/O with the solves (the job driver):
+ * streams are created non-blocking; host buffers of the async copies must be pinned. */
+int tvl1_set_device(int device);                        /* binds the calling host thread to the device */
+int tvl1_stream_create(int device, void** out_stream);
+int tvl1_stream_destroy(void* stream);
+int tvl1_stream_sync(void* stream);
+int tvl1_stream_query(void* stream);                    /* 1: all work done, 0: still running, < 0: error */
+int tvl1_stream_wait(void* waiter, void* signaller);    /* waiter's later work runs after signaller's earlier work */
+int tvl1_dev_h2d_async(void* d_dst, const void* h_src, size_t bytes, void* stream);
+int tvl1_dev_d2h_async(void* h_dst, const void* d_src, size_t bytes, void* stream);
 int tvl1_host_alloc_pinned(size_t bytes, void** out);
 int tvl1_host_free_pinned(void* p);
 
