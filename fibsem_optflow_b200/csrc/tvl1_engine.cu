@@ -65,6 +65,41 @@ static int upload_cubic_table(int device)
     return TVL1_OK;
 }
 
+// ---------------------------------------------------------------- tensor maps (TMA)
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point: the library keeps linking the CUDA
+// runtime only (statically), never libcuda
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn tensor_map_encoder()
+{
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+
+// an fp32 plane {pitch x h} as a 2-D tensor whose box is one staged tile (box_w x box_h elements, dense rows)
+int make_plane_map(CUtensorMap* tm, const float* base, int pitch, int h, int box_w, int box_h)
+{
+    EncodeTiledFn enc = tensor_map_encoder();
+    if (!enc) return fail(TVL1_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t dims[2] = {(cuuint64_t)pitch, (cuuint64_t)h};
+    const cuuint64_t strides[1] = {(cuuint64_t)pitch * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)box_w, (cuuint32_t)box_h}, es[2] = {1, 1};
+    const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, es,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(TVL1_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for a %dx%d plane", (int)r, pitch, h);
+    return TVL1_OK;
+}
+
 // ---------------------------------------------------------------- pyramid geometry (A.2)
 
 static int scaled_size(int n, double f) { return (int)lrint((double)n * f); }   // round half even
@@ -203,7 +238,8 @@ static int tile_rows_search(int w, int h, int strip, int halo, int rmin, int res
     double best = -1.0;
     int best_r = rmin;
     long long best_g = 1;
-    for (int R = rmin; R <= 64; ++R) {
+    static const int rmax = getenv("TVL1_DEV_RMAX") ? atoi(getenv("TVL1_DEV_RMAX")) : 64;   // developer sweeps only
+    for (int R = rmin; R <= rmax; ++R) {
         const long long ntiles = ns * cdiv(h, R);
         const long long G = ntiles < slots ? ntiles : slots;   // warps that get work
         const long long rounds = (ntiles + G - 1) / G;
@@ -338,6 +374,7 @@ int launch_median(const MedianArgs& a, int planes, cudaStream_t st)
 // ---------------------------------------------------------------- handle
 
 struct Level {
+    alignas(64) CUtensorMap tm_med[2][2];   // median tiles of [u1 | u2][twin] (built with the arena)
     int w, h, pitch;
     float *I0, *I1, *u1, *u2;   // u1/u2: buffer [0] of the twin pair; [1] is shared scratch
 };
@@ -457,6 +494,15 @@ static int ensure_capacity(tvl1_handle* H, int w, int h, cudaStream_t st)
     H->d_partials = (double*)(H->arena + o_part);
     H->partials_cap = nb;
     H->d_ctrl = (Ctrl*)(H->arena + o_ctrl);
+    for (int s = 0; s < L; s++) {   // tensor maps of the planes TMA reads, once per arena
+        Level& lv = H->lv[s];
+        const float* planes[2][2] = {{lv.u1, H->u1x}, {lv.u2, H->u2x}};
+        for (int z = 0; z < 2; z++)
+            for (int t = 0; t < 2; t++) {
+                const int r = make_plane_map(&lv.tm_med[z][t], planes[z][t], lv.pitch, lv.h, TVL1_MED_SW, TVL1_MED_SH);
+                if (r) { release_arena(H); return r; }
+            }
+    }
     H->cap_w = w; H->cap_h = h; H->cap_scales = H->prm.nscales; H->cap_step = H->prm.scale_step;
     // pad columns are read (never used) by the vectorised kernels: give them defined contents.  On the
     // solve's own stream: a non-blocking stream does not order itself after the legacy default stream
@@ -580,6 +626,7 @@ static int calc_device(tvl1_handle* H, const uint8_t* f0, size_t pitch0, const u
         MedianArgs ma;
         ma.u1[0] = lv.u1; ma.u1[1] = H->u1x; ma.u2[0] = lv.u2; ma.u2[1] = H->u2x;
         ma.w = lv.w; ma.h = lv.h; ma.pitch = lv.pitch; ma.level = s; ma.ctrl = H->d_ctrl;
+        memcpy(ma.tm, lv.tm_med, sizeof(ma.tm));
         WarpArgs wa;
         wa.I0 = lv.I0; wa.I1 = lv.I1;
         wa.u1[0] = lv.u1; wa.u1[1] = H->u1x; wa.u2[0] = lv.u2; wa.u2[1] = H->u2x;
@@ -1170,6 +1217,8 @@ int tvl1_k_median5(const float* d_src, int w, int h, int pitch, float* d_dst, vo
     MedianArgs a;
     a.u1[0] = const_cast<float*>(d_src); a.u1[1] = d_dst; a.u2[0] = a.u2[1] = nullptr;
     a.w = w; a.h = h; a.pitch = pitch; a.level = -1; a.slot = 0; a.ctrl = nullptr;
+    memset(a.tm, 0, sizeof(a.tm));
+    if (int r = make_plane_map(&a.tm[0][0], d_src, pitch, h, TVL1_MED_SW, TVL1_MED_SH)) return r;
     stage_begin((cudaStream_t)stream);
     const int rc = launch_median(a, 1, (cudaStream_t)stream);
     stage_end((cudaStream_t)stream);
