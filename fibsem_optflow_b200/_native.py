@@ -64,6 +64,7 @@ class StackIO(C.Structure):
         ("npoints", C.c_int), ("scale", C.c_float), ("seed", C.c_longlong),
         ("px", C.c_void_p), ("py", C.c_void_p), ("qx", C.c_void_p), ("qy", C.c_void_p), ("w", C.c_void_p),
         ("n_out", C.c_void_p), ("stats", C.POINTER(Stats)), ("prescale", C.c_double),
+        ("pair_p", C.POINTER(C.c_int)), ("pair_q", C.POINTER(C.c_int)), ("n_pairs", C.c_int),
     ]
 
 
@@ -365,8 +366,9 @@ class Solver:
         return px[:k], py[:k], qx[:k], qy[:k], wg[:k], pos[:k]
 
     def run_stack(self, slices, flows=True, apply_mask=False, npoints=-1, scale=0.5, seed=-1,
-                  out_u=None, out_v=None, slice_ptrs=None, pitch=None, shape=None, prescale=0.0):
-        """Pairs (k, k+1) of a stack of uint8 slices (tvl1_stack_run).  Returns a dict with
+                  out_u=None, out_v=None, slice_ptrs=None, pitch=None, shape=None, prescale=0.0, pairs=None):
+        """Pairs (k, k+1) of a stack of uint8 slices -- or the explicit `pairs` [(p, q), ...] of slice
+        indices -- through tvl1_stack_run.  Returns a dict with
         'u', 'v' (lists of planes, if flows), 'matches' (per pair px,py,qx,qy,w, if npoints >= 0),
         'stats' (per pair), 'ms' (CUDA-event time of the whole stack).  slice_ptrs/out_u/out_v let
         the caller pass pinned host memory (bench.py); otherwise NumPy arrays are used."""
@@ -378,8 +380,12 @@ class Solver:
         else:
             h, w = shape
         n = len(slice_ptrs)
-        npairs = n - 1
+        npairs = n - 1 if pairs is None else len(pairs)
         io = StackIO()
+        if pairs is not None:   # explicit (p, q) slice indices instead of the chain (k, k+1)
+            ap = (C.c_int * npairs)(*[int(p) for p, _ in pairs])
+            aq = (C.c_int * npairs)(*[int(q) for _, q in pairs])
+            io.pair_p, io.pair_q, io.n_pairs = ap, aq, npairs
         arr = (C.c_void_p * n)(*slice_ptrs)
         io.h_slices = arr
         io.pitch = pitch

@@ -375,6 +375,7 @@ int launch_median(const MedianArgs& a, int planes, cudaStream_t st)
 
 struct Level {
     alignas(64) CUtensorMap tm_med[2][2];   // median tiles of [u1 | u2][twin] (built with the arena)
+    CUtensorMap tm_I1[2];                   // warp windows of I1: RW x 16 and RW x RH boxes
     int w, h, pitch;
     float *I0, *I1, *u1, *u2;   // u1/u2: buffer [0] of the twin pair; [1] is shared scratch
 };
@@ -382,6 +383,8 @@ struct Level {
 }  // namespace tvl1
 
 using namespace tvl1;
+
+#define TVL1_STACK_SLOTS 4   // slice slots of tvl1_stack_run: two for the pair being solved, two for the next pair's frames
 
 struct tvl1_handle {
     int device = 0;
@@ -416,14 +419,14 @@ struct tvl1_handle {
     // sampler scratch (tvl1_sampler.cu)
     void* samp = nullptr;
     // stack runner (tvl1_stack_run): 3 slice slots, 2 flow buffers, copy streams
-    uint8_t* st_slice[3] = {nullptr, nullptr, nullptr};
+    uint8_t* st_slice[TVL1_STACK_SLOTS] = {};
     uint8_t* st_raw[2] = {nullptr, nullptr};   // raw slices awaiting the device prescale
     size_t st_raw_bytes = 0;
     float* st_flow[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
     size_t st_pitch8 = 0;
     int st_w = 0, st_h = 0;
     cudaStream_t st_in = nullptr, st_out = nullptr;
-    cudaEvent_t st_up[3] = {nullptr, nullptr, nullptr}, st_ready[2] = {nullptr, nullptr}, st_down[2] = {nullptr, nullptr};
+    cudaEvent_t st_up[TVL1_STACK_SLOTS] = {}, st_ready[2] = {nullptr, nullptr}, st_down[2] = {nullptr, nullptr};
 };
 
 namespace tvl1 {
@@ -502,6 +505,10 @@ static int ensure_capacity(tvl1_handle* H, int w, int h, cudaStream_t st)
                 const int r = make_plane_map(&lv.tm_med[z][t], planes[z][t], lv.pitch, lv.h, TVL1_MED_SW, TVL1_MED_SH);
                 if (r) { release_arena(H); return r; }
             }
+        for (int k = 0; k < 2; k++) {
+            const int r = make_plane_map(&lv.tm_I1[k], lv.I1, lv.pitch, lv.h, TVL1_WP_RW, k == 0 ? 16 : TVL1_WP_RH);
+            if (r) { release_arena(H); return r; }
+        }
     }
     H->cap_w = w; H->cap_h = h; H->cap_scales = H->prm.nscales; H->cap_step = H->prm.scale_step;
     // pad columns are read (never used) by the vectorised kernels: give them defined contents.  On the
@@ -632,6 +639,7 @@ static int calc_device(tvl1_handle* H, const uint8_t* f0, size_t pitch0, const u
         wa.u1[0] = lv.u1; wa.u1[1] = H->u1x; wa.u2[0] = lv.u2; wa.u2[1] = H->u2x;
         wa.I1w = nullptr; wa.I1wx = H->I1wx; wa.I1wy = H->I1wy; wa.grad = nullptr; wa.rho_c = H->rho;
         wa.w = lv.w; wa.h = lv.h; wa.pitch = lv.pitch; wa.level = s; wa.ctrl = H->d_ctrl;
+        memcpy(wa.tmI1, lv.tm_I1, sizeof(wa.tmI1));
 
         for (int wi = 0; wi < W; ++wi) {
             const int slot = s * W + wi;
@@ -838,7 +846,7 @@ void tvl1_destroy(tvl1_handle* H)
     if (H->d_uo) cudaFree(H->d_uo);
     if (H->d_vo) cudaFree(H->d_vo);
     tvl1::sampler_release(H->samp);
-    for (int i = 0; i < 3; i++) { if (H->st_slice[i]) cudaFree(H->st_slice[i]); if (H->st_up[i]) cudaEventDestroy(H->st_up[i]); }
+    for (int i = 0; i < TVL1_STACK_SLOTS; i++) { if (H->st_slice[i]) cudaFree(H->st_slice[i]); if (H->st_up[i]) cudaEventDestroy(H->st_up[i]); }
     for (int i = 0; i < 2; i++) if (H->st_raw[i]) cudaFree(H->st_raw[i]);
     for (int i = 0; i < 2; i++) {
         for (int j = 0; j < 2; j++) if (H->st_flow[i][j]) cudaFree(H->st_flow[i][j]);
@@ -951,19 +959,19 @@ static int stack_reserve(tvl1_handle* H, int w, int h)
     if (!H->st_in) {
         CK(cudaStreamCreateWithFlags(&H->st_in, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&H->st_out, cudaStreamNonBlocking));
-        for (int i = 0; i < 3; i++) CK(cudaEventCreateWithFlags(&H->st_up[i], cudaEventDisableTiming));
+        for (int i = 0; i < TVL1_STACK_SLOTS; i++) CK(cudaEventCreateWithFlags(&H->st_up[i], cudaEventDisableTiming));
         for (int i = 0; i < 2; i++) {
             CK(cudaEventCreateWithFlags(&H->st_ready[i], cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&H->st_down[i], cudaEventDisableTiming));
         }
     }
     if (H->st_w == w && H->st_h == h) return TVL1_OK;
-    for (int i = 0; i < 3; i++) { if (H->st_slice[i]) cudaFree(H->st_slice[i]); H->st_slice[i] = nullptr; }
+    for (int i = 0; i < TVL1_STACK_SLOTS; i++) { if (H->st_slice[i]) cudaFree(H->st_slice[i]); H->st_slice[i] = nullptr; }
     for (int i = 0; i < 2; i++)
         for (int j = 0; j < 2; j++) { if (H->st_flow[i][j]) cudaFree(H->st_flow[i][j]); H->st_flow[i][j] = nullptr; }
     H->st_w = H->st_h = 0;
     H->st_pitch8 = (size_t)round_up(w, 128);
-    for (int i = 0; i < 3; i++) CK(cudaMalloc(&H->st_slice[i], H->st_pitch8 * h));
+    for (int i = 0; i < TVL1_STACK_SLOTS; i++) CK(cudaMalloc(&H->st_slice[i], H->st_pitch8 * h));
     for (int i = 0; i < 2; i++)
         for (int j = 0; j < 2; j++) CK(cudaMalloc(&H->st_flow[i][j], (size_t)w * h * sizeof(float)));
     H->st_w = w; H->st_h = h;
@@ -977,14 +985,21 @@ int tvl1_stack_run(tvl1_handle* H, const tvl1_stack_io* io, float* ms_total)
     const int rw = io->width, rh = io->height;          // size of the slices as given
     int w = rw, h = rh;                                 // size the solver works at
     const bool pre = io->prescale > 0.0 && io->prescale != 1.0;
+    const bool listed = io->pair_p != nullptr || io->pair_q != nullptr;   // explicit (p, q) pairs instead of (k, k+1)
     if (!io->h_slices || n < 2 || rw <= 0 || rh <= 0 || io->pitch < (size_t)rw)
         return fail(TVL1_ERR_INVALID, "a stack needs >= 2 slices of non-zero size");
+    if (listed && (!io->pair_p || !io->pair_q || io->n_pairs < 1)) return fail(TVL1_ERR_INVALID, "pair_p, pair_q and n_pairs go together");
+    const int npairs = listed ? io->n_pairs : n - 1;
     if (pre) { int r = tvl1_prescaled_size(rw, rh, io->prescale, &w, &h); if (r) return r; }
     if ((io->h_u == nullptr) != (io->h_v == nullptr)) return fail(TVL1_ERR_INVALID, "h_u and h_v go together");
     if (io->h_u && io->pitch_out < (size_t)w * 4) return fail(TVL1_ERR_INVALID, "pitch_out smaller than a row");
     if (io->npoints >= 0 && (!io->px || !io->py || !io->qx || !io->qy || !io->w || !io->n_out))
         return fail(TVL1_ERR_INVALID, "match output arrays missing");
     for (int k = 0; k < n; k++) if (!io->h_slices[k]) return fail(TVL1_ERR_INVALID, "slice %d is null", k);
+    auto pp = [&](int k) { return listed ? io->pair_p[k] : k; };
+    auto pq = [&](int k) { return listed ? io->pair_q[k] : k + 1; };
+    for (int k = 0; k < npairs; k++)
+        if (pp(k) < 0 || pp(k) >= n || pq(k) < 0 || pq(k) >= n) return fail(TVL1_ERR_INVALID, "pair %d names a slice outside the stack", k);
     CK(cudaSetDevice(H->device));
     int rc = stack_reserve(H, w, h);
     if (rc) return rc;
@@ -1008,28 +1023,52 @@ int tvl1_stack_run(tvl1_handle* H, const tvl1_stack_io* io, float* ms_total)
     CK(cudaEventCreate(&tev.b));
     cudaEvent_t t0 = tev.a, t1 = tev.b;
     CK(cudaEventRecord(t0, cs));
-    auto upload = [&](int k) -> int {
-        const int s = k % 3;
-        if (!pre) {
-            CK(cudaMemcpy2DAsync(H->st_slice[s], p8, io->h_slices[k], io->pitch, w, h, cudaMemcpyHostToDevice, H->st_in));
-        } else {
-            // raw slice -> device, then the loader's 8-bit resize (src/optflow.cpp:111,124) on the
-            // copy stream: the solver never sees the raw size.  Two staging buffers, re-used in stream
-            // order (slice k+2's upload follows slice k's prescale on the same stream)
-            uint8_t* raw = H->st_raw[k & 1];
-            CK(cudaMemcpy2DAsync(raw, (size_t)rw, io->h_slices[k], io->pitch, rw, rh, cudaMemcpyHostToDevice, H->st_in));
-            int r = tvl1_prescale_u8(raw, (size_t)rw, rw, rh, io->prescale, H->st_slice[s], p8, H->st_in);
-            if (r) return r;
+    // Device slots for the (prescaled) slices, kept by slice index: the slice two adjacent pairs share goes
+    // up once (src/optflow.cpp:97-103), and the frames of pair k+1 arrive on the copy stream while pair k is
+    // being solved.  `held[s]`: last pair that reads slot s -- a slot is only refilled once that pair's solve
+    // has completed (the solves are synchronous to the host, so "completed" is known here).
+    const int NS = TVL1_STACK_SLOTS;
+    int tag[NS], held[NS];
+    for (int s = 0; s < NS; s++) { tag[s] = -1; held[s] = -1; }
+    int uploads = 0;
+    auto find = [&](int slice) { for (int s = 0; s < NS; s++) if (tag[s] == slice) return s; return -1; };
+    // slot for `slice` if it is resident or can be brought in without touching what pair `busy` still reads
+    auto stage = [&](int slice, int for_pair, int busy, int* out) -> int {
+        int s = find(slice);
+        if (s < 0) {
+            for (int c = 0; c < NS; c++)
+                if (held[c] < busy && (s < 0 || held[c] < held[s])) s = c;
+            if (s < 0) { *out = -1; return TVL1_OK; }   // every slot is still in use: later
+            tag[s] = slice;
+            if (!pre) {
+                CK(cudaMemcpy2DAsync(H->st_slice[s], p8, io->h_slices[slice], io->pitch, w, h, cudaMemcpyHostToDevice, H->st_in));
+            } else {
+                // raw slice -> device, then the loader's 8-bit resize (src/optflow.cpp:111,124) on the
+                // copy stream: the solver never sees the raw size.  Two staging buffers, re-used in stream
+                // order (an upload follows the prescale that last read the buffer, on the same stream)
+                uint8_t* raw = H->st_raw[uploads & 1];
+                CK(cudaMemcpy2DAsync(raw, (size_t)rw, io->h_slices[slice], io->pitch, rw, rh, cudaMemcpyHostToDevice, H->st_in));
+                int r = tvl1_prescale_u8(raw, (size_t)rw, rw, rh, io->prescale, H->st_slice[s], p8, H->st_in);
+                if (r) return r;
+            }
+            uploads++;
+            CK(cudaEventRecord(H->st_up[s], H->st_in));
         }
-        CK(cudaEventRecord(H->st_up[s], H->st_in));
+        if (held[s] < for_pair) held[s] = for_pair;
+        *out = s;
         return TVL1_OK;
     };
-    if ((rc = upload(0)) || (rc = upload(1))) return rc;
     long long rand_skip = 0;
-    for (int k = 0; k + 1 < n; k++) {
-        const int s0 = k % 3, s1 = (k + 1) % 3, fb = k & 1;
-        // slice k+2 goes into the slot pair k-1 read its first frame from; that solve has completed
-        if (k + 2 < n && (rc = upload(k + 2))) return rc;
+    for (int k = 0; k < npairs; k++) {
+        const int fb = k & 1;
+        int s0 = -1, s1 = -1, tmp = -1;
+        // this pair's frames (pair k-1 has completed: only pair k itself pins slots now)
+        if ((rc = stage(pp(k), k, k, &s0)) || (rc = stage(pq(k), k, k, &s1))) return rc;
+        if (s0 < 0 || s1 < 0) return fail(TVL1_ERR_CUDA, "no free slice slot (internal)");
+        // the next pair's frames go up now, into slots this pair does not read
+        if (k + 1 < npairs) {
+            if ((rc = stage(pp(k + 1), k + 1, k + 1, &tmp)) || (rc = stage(pq(k + 1), k + 1, k + 1, &tmp))) return rc;
+        }
         CK(cudaStreamWaitEvent(cs, H->st_up[s0], 0));
         CK(cudaStreamWaitEvent(cs, H->st_up[s1], 0));
         if (k >= 2 && io->h_u) CK(cudaStreamWaitEvent(cs, H->st_down[fb], 0));   // flow buffer still draining
@@ -1048,6 +1087,8 @@ int tvl1_stack_run(tvl1_handle* H, const tvl1_stack_io* io, float* ms_total)
                                           &io->n_out[k], &used, cs);
             if (rc) return rc;
             rand_skip += used;
+        } else if (io->apply_mask) {
+            CK(cudaStreamSynchronize(cs));   // slot s1 is read by the mask kernel: done before it can be refilled
         }
         if (io->h_u) {
             CK(cudaEventRecord(H->st_ready[fb], cs));
@@ -1120,6 +1161,8 @@ int tvl1_k_warp(const float* d_I0, const float* d_I1, const float* d_u1, const f
     a.u1[0] = a.u1[1] = d_u1; a.u2[0] = a.u2[1] = d_u2;
     a.I1w = d_I1w; a.I1wx = d_I1wx; a.I1wy = d_I1wy; a.grad = d_grad; a.rho_c = d_rho_c;
     a.w = w; a.h = h; a.pitch = pitch; a.level = -1; a.ctrl = nullptr;
+    for (int k = 0; k < 2; k++)
+        if ((rc = make_plane_map(&a.tmI1[k], d_I1, pitch, h, TVL1_WP_RW, k == 0 ? 16 : TVL1_WP_RH))) return rc;
     stage_begin((cudaStream_t)stream);
     rc = launch_warp(a, (cudaStream_t)stream);
     stage_end((cudaStream_t)stream);

@@ -181,6 +181,11 @@ typedef struct tvl1_stack_io {
                                          exactly like the loader's cv::resize (src/optflow.cpp:111,124);
                                          width/height/pitch describe the slices as given, the flow
                                          planes have tvl1_prescaled_size(width, height, prescale) */
+    const int* pair_p;                /* NULL: pairs (k, k+1).  Otherwise n_pairs explicit pairs            */
+    const int* pair_q;                /* (slices[pair_p[k]], slices[pair_q[k]]) -- the "images" list of a  */
+    int n_pairs;                      /* job (src/optflow.cpp:86-94); outputs are indexed by pair.  A slice */
+                                      /* consecutive pairs share stays on the device; the next pair's frames */
+                                      /* go up while the current pair is solved                              */
 } tvl1_stack_io;
 
 int tvl1_stack_run(tvl1_handle* h, const tvl1_stack_io* io, float* ms_total);

@@ -76,3 +76,25 @@ def test_stack_prescale_on_device(gpu, orc, scale):
         for j in range(5):
             assert np.array_equal(res["matches"][k][j], want[j])
     s.close()
+
+
+def test_stack_explicit_pairs(gpu, orc):
+    """tvl1_stack_io.pair_p / pair_q: the "images" list of a job -- independent pairs, a repeated pair, a
+    reversed pair and a chained one -- through the pipelined runner (4 slice slots, next pair's frames
+    uploaded during the current solve): flows and matches equal per-pair oracle solves."""
+    slices = synth.make_stack(5, 72, 100, seed=17)        # 6 slices
+    pairs = [(0, 1), (2, 3), (4, 5), (5, 4), (4, 5), (1, 2), (2, 3), (0, 5)]
+    s = gpu.Solver(gpu.default_params(lambda_=0.15, nscales=3))
+    res = s.run_stack(slices, flows=True, apply_mask=True, npoints=10, scale=0.5, seed=9, pairs=pairs)
+    assert len(res["u"]) == len(pairs)
+    for k, (p, q) in enumerate(pairs):
+        ou, ov, oit, lev = orc.tvl1_calc(slices[p], slices[q], **{"lambda": 0.15, "nscales": 3})
+        orc.mask_flow(slices[q], ou, ov)
+        assert np.array_equal(res["stats"][k].iters_array(), oit[:lev]), k
+        assert np.array_equal(res["u"][k], ou) and np.array_equal(res["v"][k], ov), k
+        want = orc.random_points(slices[p], slices[q], ou, ov, scale=0.5, npoints=10, seed=9)
+        for j in range(5):
+            assert np.array_equal(res["matches"][k][j], want[j]), (k, j)
+    with pytest.raises(gpu.Tvl1Error):
+        s.run_stack(slices, pairs=[(0, 6)])
+    s.close()
