@@ -56,6 +56,14 @@ class Stats(C.Structure):
         return [(self.width[i], self.height[i]) for i in range(self.levels)]
 
 
+class FeatureParams(C.Structure):
+    _fields_ = [
+        ("nfeatures", C.c_int), ("scale_factor", C.c_float), ("nlevels", C.c_int), ("edge_threshold", C.c_int),
+        ("first_level", C.c_int), ("patch_size", C.c_int), ("fast_threshold", C.c_int), ("ratio", C.c_float),
+        ("ransac", C.c_double), ("homo", C.c_int), ("debug", C.c_int), ("reserved", C.c_int * 4),
+    ]
+
+
 class StackIO(C.Structure):
     _fields_ = [
         ("h_slices", C.POINTER(C.c_void_p)), ("pitch", C.c_size_t),
@@ -73,7 +81,8 @@ EXPORTS = [
     "tvl1_version", "tvl1_last_error", "tvl1_default_params", "tvl1_create", "tvl1_destroy",
     "tvl1_set_params", "tvl1_set_option", "tvl1_set_timing", "tvl1_calc_u8", "tvl1_calc_u8_host",
     "tvl1_prescaled_size", "tvl1_prescale_u8", "tvl1_prescale_u8_host",
-    "tvl1_mask_flow_u8", "tvl1_finish_flow_u8", "tvl1_sample_matches", "tvl1_sample_matches_skip", "tvl1_stack_run", "tvl1_k_convert_u8", "tvl1_k_resize",
+    "tvl1_mask_flow_u8", "tvl1_finish_flow_u8", "tvl1_sample_matches", "tvl1_sample_matches_skip", "tvl1_sample_matches_ex",
+    "tvl1_default_feature_params", "tvl1_find_alignment", "tvl1_warp_affine_u8", "tvl1_warp_affine_f32", "tvl1_stack_run", "tvl1_k_convert_u8", "tvl1_k_resize",
     "tvl1_k_centered_gradient", "tvl1_k_warp", "tvl1_k_iterate", "tvl1_k_iterate_fused2", "tvl1_k_outer", "tvl1_k_median5", "tvl1_k_last_ms",
     "tvl1_pyramid_sizes", "tvl1_glibc_rand", "tvl1_selftest_arith", "tvl1_dev_count", "tvl1_dev_alloc", "tvl1_dev_free",
     "tvl1_dev_memset", "tvl1_dev_h2d", "tvl1_dev_d2h", "tvl1_dev_sync", "tvl1_set_device", "tvl1_stream_create",
@@ -123,6 +132,16 @@ def lib():
                                       C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int,
                                       C.c_longlong, _vp, _vp, _vp, _vp, _vp, _vp,
                                       C.POINTER(C.c_int), _vp]
+    L.tvl1_sample_matches_ex.argtypes = [_vp, _vp, _sz, _vp, _sz, _vp, _vp, _sz, C.c_int, C.c_int,
+                                         C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int,
+                                         C.c_longlong, C.c_longlong, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp,
+                                         C.POINTER(C.c_int), C.POINTER(C.c_longlong), _vp]
+    L.tvl1_default_feature_params.argtypes = [C.POINTER(FeatureParams)]
+    L.tvl1_default_feature_params.restype = None
+    L.tvl1_find_alignment.argtypes = [_vp, _vp, _sz, C.c_int, C.c_int, _vp, _sz, C.c_int, C.c_int,
+                                      C.POINTER(FeatureParams), _vp, C.POINTER(C.c_int), C.POINTER(C.c_int), _vp]
+    L.tvl1_warp_affine_u8.argtypes = [_vp, _sz, C.c_int, C.c_int, _vp, _vp, _sz, C.c_int, C.c_int, _vp]
+    L.tvl1_warp_affine_f32.argtypes = [_vp, _sz, C.c_int, C.c_int, _vp, _vp, _sz, C.c_int, C.c_int, _vp]
     L.tvl1_stack_run.argtypes = [_vp, C.POINTER(StackIO), C.POINTER(C.c_float)]
     L.tvl1_k_convert_u8.argtypes = [_vp, _sz, C.c_int, C.c_int, _vp, C.c_int, _vp]
     L.tvl1_k_resize.argtypes = [_vp, C.c_int, C.c_int, C.c_int, _vp, C.c_int, C.c_int, C.c_int,
@@ -350,18 +369,44 @@ class Solver:
         """output_type "map": + coordinate grid; then flow = 0 where frame1 <= 1 (src/optflow.cpp:445-473)"""
         check(lib().tvl1_finish_flow_u8(self.handle, d_f1, pitch1, w, h, d_u, d_v, pitch_out, int(bool(add_grid)), stream))
 
+    def find_alignment(self, moving, fixed, **kw):
+        """find_alignment (src/features.cpp:46-167): host uint8 frames in, (affine 2x3 float32 mapping `moving`
+        coordinates to `fixed` coordinates, n_matches, n_good) out.  kw: fields of tvl1_feature_params."""
+        moving = np.ascontiguousarray(moving, np.uint8)
+        fixed = np.ascontiguousarray(fixed, np.uint8)
+        p = FeatureParams()
+        lib().tvl1_default_feature_params(C.byref(p))
+        for k, v in kw.items():
+            k = {"scaleFactor": "scale_factor", "edgeThreshold": "edge_threshold", "firstLevel": "first_level",
+                 "patchSize": "patch_size", "fastThreshold": "fast_threshold"}.get(k, k)
+            if not hasattr(p, k):
+                raise KeyError(k)
+            setattr(p, k, v)
+        bm = DevBuf(moving.nbytes, self.device).upload(moving)
+        bf = DevBuf(fixed.nbytes, self.device).upload(fixed)
+        aff = np.zeros(6, np.float32)
+        nm, ng = C.c_int(0), C.c_int(0)
+        try:
+            check(lib().tvl1_find_alignment(self.handle, bm.ptr, moving.shape[1], moving.shape[1], moving.shape[0],
+                                            bf.ptr, fixed.shape[1], fixed.shape[1], fixed.shape[0], C.byref(p),
+                                            aff.ctypes.data, C.byref(nm), C.byref(ng), None))
+        finally:
+            bm.free()
+            bf.free()
+        return aff.reshape(2, 3), nm.value, ng.value
+
     def sample_matches_device(self, d_f0, pitch0, d_f1, pitch1, d_u, d_v, pitch_flow, w, h,
                               roi0=(0, 0), roi1=(0, 0), scale=0.5, npoints=25, seed=-1,
-                              stream=None):
+                              stream=None, q_is_map=False):
         n = max(int(npoints), 1)
         px, py, qx, qy, wg = (np.zeros(n, np.float64) for _ in range(5))
         pos = np.zeros((n, 2), np.int32)
         k = C.c_int(0)
-        check(lib().tvl1_sample_matches(self.handle, d_f0, pitch0, d_f1, pitch1, d_u, d_v,
-                                        pitch_flow, w, h, roi0[0], roi0[1], roi1[0], roi1[1],
-                                        scale, npoints, seed, px.ctypes.data, py.ctypes.data,
-                                        qx.ctypes.data, qy.ctypes.data, wg.ctypes.data,
-                                        pos.ctypes.data, C.byref(k), stream))
+        check(lib().tvl1_sample_matches_ex(self.handle, d_f0, pitch0, d_f1, pitch1, d_u, d_v,
+                                           pitch_flow, w, h, roi0[0], roi0[1], roi1[0], roi1[1],
+                                           scale, npoints, seed, 0, int(bool(q_is_map)), px.ctypes.data, py.ctypes.data,
+                                           qx.ctypes.data, qy.ctypes.data, wg.ctypes.data,
+                                           pos.ctypes.data, C.byref(k), None, stream))
         k = k.value
         return px[:k], py[:k], qx[:k], qy[:k], wg[:k], pos[:k]
 
@@ -501,6 +546,29 @@ def k_iterate(I1wx, I1wy, grad, rho_c, u1, u2, p11, p12, p21, p22, l_t, theta, t
     check(fn(*[p.ptr for p in consts], *[p.ptr for p in state], w, h,
              state[0].pitch, l_t, theta, taut, n, errs.ctypes.data, None))
     return tuple(p.get() for p in state) + (errs[:n],)
+
+
+def warp_affine(src, affine, dsize, device=0):
+    """cv::warpAffine(src, affine, dsize = (w, h), INTER_LINEAR, BORDER_CONSTANT 0) on the device; uint8 or float32"""
+    src = np.ascontiguousarray(src)
+    aff = np.ascontiguousarray(affine, np.float32).reshape(6)
+    dw, dh = int(dsize[0]), int(dsize[1])
+    sh, sw = src.shape
+    bs = DevBuf(src.nbytes, device).upload(src)
+    if src.dtype == np.uint8:
+        bd = DevBuf(dw * dh, device)
+        check(lib().tvl1_warp_affine_u8(bs.ptr, sw, sw, sh, aff.ctypes.data, bd.ptr, dw, dw, dh, None))
+        check(lib().tvl1_dev_sync(device))
+        out = bd.download((dh, dw), np.uint8)
+    else:
+        assert src.dtype == np.float32
+        bd = DevBuf(dw * dh * 4, device)
+        check(lib().tvl1_warp_affine_f32(bs.ptr, sw * 4, sw, sh, aff.ctypes.data, bd.ptr, dw * 4, dw, dh, None))
+        check(lib().tvl1_dev_sync(device))
+        out = bd.download((dh, dw), np.float32)
+    bs.free()
+    bd.free()
+    return out
 
 
 def k_median5(src, device=0):

@@ -65,6 +65,15 @@ static int upload_cubic_table(int device)
     return TVL1_OK;
 }
 
+int copy_words(const void* src, void* dst, int n32, cudaStream_t st)
+{
+    if (n32 <= 0) return TVL1_OK;
+    const int blocks = n32 <= 256 ? 1 : (n32 + 1023) / 1024 < 32 ? (n32 + 1023) / 1024 : 32;
+    k_copy_words<<<blocks, n32 < 256 ? 32 : 256, 0, st>>>((const int*)src, (int*)dst, n32);
+    CK(cudaGetLastError());
+    return TVL1_OK;
+}
+
 // ---------------------------------------------------------------- tensor maps (TMA)
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point: the library keeps linking the CUDA
@@ -416,8 +425,9 @@ struct tvl1_handle {
     cudaStream_t own_stream = nullptr;
     std::vector<cudaEvent_t> events;
     size_t ev_used = 0;
-    // sampler scratch (tvl1_sampler.cu)
+    // sampler scratch (tvl1_sampler.cu), feature scratch (tvl1_features.cu)
     void* samp = nullptr;
+    void* feat = nullptr;
     // stack runner (tvl1_stack_run): 3 slice slots, 2 flow buffers, copy streams
     uint8_t* st_slice[TVL1_STACK_SLOTS] = {};
     uint8_t* st_raw[2] = {nullptr, nullptr};   // raw slices awaiting the device prescale
@@ -433,6 +443,7 @@ namespace tvl1 {
 
 int handle_device(const tvl1_handle* h) { return h->device; }
 void** handle_sampler_slot(tvl1_handle* h) { return &h->samp; }
+void** handle_feature_slot(tvl1_handle* h) { return &h->feat; }
 
 static int get_event(tvl1_handle* H, cudaEvent_t* out)
 {
@@ -706,7 +717,7 @@ static int calc_device(tvl1_handle* H, const uint8_t* f0, size_t pitch0, const u
                             if ((rc = launch_iterate(i3, st))) return rc;
                         launches += want;
                     }
-                    CK(cudaMemcpyAsync(H->h_ctrl, H->d_ctrl, hdr, cudaMemcpyDeviceToHost, st));
+                    if ((rc = copy_words(H->d_ctrl, H->h_ctrl, (int)(hdr / 4), st))) return rc;   // no copy engine: see copy_words
                     CK(cudaStreamSynchronize(st));
                     done_inner = H->h_ctrl->inner;
                     if (H->h_ctrl->done || done_inner >= H->inner) break;
@@ -743,7 +754,7 @@ static int calc_device(tvl1_handle* H, const uint8_t* f0, size_t pitch0, const u
         CK(cudaMemcpy2DAsync(d_v, pitch_out, uc ? H->u2x : l0.u2, (size_t)l0.pitch * 4, (size_t)w * 4, h, cudaMemcpyDeviceToDevice, st));
     }
     CK(cudaEventRecord(ev_end, st));
-    CK(cudaMemcpyAsync(H->h_ctrl, H->d_ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
+    if ((rc = copy_words(H->d_ctrl, H->h_ctrl, (int)(sizeof(Ctrl) / 4), st))) return rc;
     CK(cudaStreamSynchronize(st));
 
     if (stats) {
@@ -846,6 +857,7 @@ void tvl1_destroy(tvl1_handle* H)
     if (H->d_uo) cudaFree(H->d_uo);
     if (H->d_vo) cudaFree(H->d_vo);
     tvl1::sampler_release(H->samp);
+    tvl1::features_release(H->feat);
     for (int i = 0; i < TVL1_STACK_SLOTS; i++) { if (H->st_slice[i]) cudaFree(H->st_slice[i]); if (H->st_up[i]) cudaEventDestroy(H->st_up[i]); }
     for (int i = 0; i < 2; i++) if (H->st_raw[i]) cudaFree(H->st_raw[i]);
     for (int i = 0; i < 2; i++) {
@@ -1032,7 +1044,8 @@ int tvl1_stack_run(tvl1_handle* H, const tvl1_stack_io* io, float* ms_total)
     for (int s = 0; s < NS; s++) { tag[s] = -1; held[s] = -1; }
     int uploads = 0;
     auto find = [&](int slice) { for (int s = 0; s < NS; s++) if (tag[s] == slice) return s; return -1; };
-    // slot for `slice` if it is resident or can be brought in without touching what pair `busy` still reads
+    // slot for `slice` if it is resident or can be brought in without touching a slot that pair `busy` (or a later
+    // one) reads
     auto stage = [&](int slice, int for_pair, int busy, int* out) -> int {
         int s = find(slice);
         if (s < 0) {
@@ -1067,7 +1080,7 @@ int tvl1_stack_run(tvl1_handle* H, const tvl1_stack_io* io, float* ms_total)
         if (s0 < 0 || s1 < 0) return fail(TVL1_ERR_CUDA, "no free slice slot (internal)");
         // the next pair's frames go up now, into slots this pair does not read
         if (k + 1 < npairs) {
-            if ((rc = stage(pp(k + 1), k + 1, k + 1, &tmp)) || (rc = stage(pq(k + 1), k + 1, k + 1, &tmp))) return rc;
+            if ((rc = stage(pp(k + 1), k + 1, k, &tmp)) || (rc = stage(pq(k + 1), k + 1, k, &tmp))) return rc;
         }
         CK(cudaStreamWaitEvent(cs, H->st_up[s0], 0));
         CK(cudaStreamWaitEvent(cs, H->st_up[s1], 0));

@@ -200,6 +200,7 @@ struct PickArgs {
     int w, h;
     int roi0x, roi0y, roi1x, roi1y;
     float inv_scale;
+    int q_is_map;       // the `features` branch of random_points (src/optflow.cpp:544-550): q = map + roi1, no pos term
     int n;
     const int* row;     // row of each target
     const int* rank;    // rank of the target among the row's set pixels
@@ -240,8 +241,8 @@ __global__ void __launch_bounds__(128) k_pick_points(const __grid_constant__ Pic
         const float fu = a.u[(size_t)y * a.pf + x], fv = a.v[(size_t)y * a.pf + x];
         const float px = (float)(x + a.roi0x) * a.inv_scale;
         const float py = (float)(y + a.roi0y) * a.inv_scale;
-        const float qx = ((float)(x + a.roi1x) + fu) * a.inv_scale;
-        const float qy = ((float)(y + a.roi1y) + fv) * a.inv_scale;
+        const float qx = a.q_is_map ? (fu + (float)a.roi1x) * a.inv_scale : ((float)(x + a.roi1x) + fu) * a.inv_scale;
+        const float qy = a.q_is_map ? (fv + (float)a.roi1y) * a.inv_scale : ((float)(y + a.roi1y) + fv) * a.inv_scale;
         a.out[0 * a.n + k] = (double)px;
         a.out[1 * a.n + k] = (double)py;
         a.out[2 * a.n + k] = (double)qx;
@@ -258,8 +259,9 @@ struct SamplerScratch {
     RandPlan* d_plan = nullptr;
     int *d_hit = nullptr, *d_jsmall = nullptr, *d_row = nullptr, *d_rank = nullptr, *d_pos = nullptr;
     double* d_out = nullptr;
-    int* h_ints = nullptr;          // pinned: hit[K], jsmall[K], pos[2K]
+    int* h_ints = nullptr;          // pinned: hit[K], jsmall[K], pos[2K], row[K], rank[K]
     double* h_out = nullptr;        // pinned: 4K
+    RandPlan* h_plan = nullptr;     // pinned
 };
 
 void sampler_release(void* p)
@@ -268,7 +270,7 @@ void sampler_release(void* p)
     if (!s) return;
     cudaFree(s->d_rowcount); cudaFreeHost(s->h_rowcount); cudaFree(s->d_plan);
     cudaFree(s->d_hit); cudaFree(s->d_jsmall); cudaFree(s->d_row); cudaFree(s->d_rank); cudaFree(s->d_pos);
-    cudaFree(s->d_out); cudaFreeHost(s->h_ints); cudaFreeHost(s->h_out);
+    cudaFree(s->d_out); cudaFreeHost(s->h_ints); cudaFreeHost(s->h_out); cudaFreeHost(s->h_plan);
     delete s;
 }
 
@@ -282,6 +284,7 @@ static int scratch_reserve(SamplerScratch* s, int h, int K)
         s->cap_h = h;
     }
     if (!s->d_plan) CKS(cudaMalloc(&s->d_plan, sizeof(RandPlan)));
+    if (!s->h_plan) CKS(cudaMallocHost(&s->h_plan, sizeof(RandPlan)));
     if (K > s->cap_k) {
         cudaFree(s->d_hit); cudaFree(s->d_jsmall); cudaFree(s->d_row); cudaFree(s->d_rank); cudaFree(s->d_pos);
         cudaFree(s->d_out); cudaFreeHost(s->h_ints); cudaFreeHost(s->h_out);
@@ -294,7 +297,7 @@ static int scratch_reserve(SamplerScratch* s, int h, int K)
         CKS(cudaMalloc(&s->d_rank, sizeof(int) * k));
         CKS(cudaMalloc(&s->d_pos, sizeof(int) * 2 * k));
         CKS(cudaMalloc(&s->d_out, sizeof(double) * 4 * k));
-        CKS(cudaMallocHost(&s->h_ints, sizeof(int) * 4 * k));
+        CKS(cudaMallocHost(&s->h_ints, sizeof(int) * 6 * k));
         CKS(cudaMallocHost(&s->h_out, sizeof(double) * 4 * k));
         s->cap_k = K;
     }
@@ -376,6 +379,17 @@ int tvl1_sample_matches_skip(tvl1_handle* H, const uint8_t* d_frame0, size_t pit
                              long long seed, long long rand_skip, double* px, double* py, double* qx, double* qy,
                              double* wgt, int* positions, int* n_out, long long* rand_used, void* stream)
 {
+    return tvl1_sample_matches_ex(H, d_frame0, pitch0, d_frame1, pitch1, d_u, d_v, pitch_flow, width, height, roi0_x, roi0_y,
+                                  roi1_x, roi1_y, scale, npoints, seed, rand_skip, 0, px, py, qx, qy, wgt, positions, n_out,
+                                  rand_used, stream);
+}
+
+int tvl1_sample_matches_ex(tvl1_handle* H, const uint8_t* d_frame0, size_t pitch0, const uint8_t* d_frame1,
+                           size_t pitch1, const float* d_u, const float* d_v, size_t pitch_flow, int width,
+                           int height, int roi0_x, int roi0_y, int roi1_x, int roi1_y, float scale, int npoints,
+                           long long seed, long long rand_skip, int q_is_map, double* px, double* py, double* qx,
+                           double* qy, double* wgt, int* positions, int* n_out, long long* rand_used, void* stream)
+{
     if (rand_used) *rand_used = 0;
     if (rand_skip < 0) return fail(TVL1_ERR_INVALID, "rand_skip must be >= 0");
     if (!H) return fail(TVL1_ERR_INVALID, "handle is null");
@@ -398,7 +412,9 @@ int tvl1_sample_matches_skip(tvl1_handle* H, const uint8_t* d_frame0, size_t pit
     // 1. per-row popcount of the mask
     k_mask_rowcount<<<(height + 7) / 8, 256, 0, st>>>(d_frame0, pitch0, d_frame1, pitch1, width, height, S->d_rowcount);
     CKS(cudaGetLastError());
-    CKS(cudaMemcpyAsync(S->h_rowcount, S->d_rowcount, sizeof(int) * (size_t)height, cudaMemcpyDeviceToHost, st));
+    // (every small transfer below goes through copy_words: pinned host memory read / written by a kernel,
+    // so that nothing queues behind a bulk flow download or slice upload on the copy engines)
+    if ((rc = copy_words(S->d_rowcount, S->h_rowcount, height, st))) return rc;
     CKS(cudaStreamSynchronize(st));
     std::vector<long long> prefix((size_t)height + 1, 0);
     for (int y = 0; y < height; y++) prefix[(size_t)y + 1] = prefix[(size_t)y] + S->h_rowcount[y];
@@ -416,9 +432,8 @@ int tvl1_sample_matches_skip(tvl1_handle* H, const uint8_t* d_frame0, size_t pit
     if (N - 1 > (long long)RCHUNK << RBITS) return fail(TVL1_ERR_UNSUPPORTED, "mask too large for the jump table");
 
     // 2. search the rand() stream for the steps that decide positions 0..K-1
-    RandPlan plan;
-    make_plan(seed, rand_skip, &plan);
-    CKS(cudaMemcpyAsync(S->d_plan, &plan, sizeof(plan), cudaMemcpyHostToDevice, st));
+    make_plan(seed, rand_skip, S->h_plan);   // (the previous call's copy has completed: it synchronised)
+    if ((rc = copy_words(S->h_plan, S->d_plan, (int)(sizeof(RandPlan) / 4), st))) return rc;
     CKS(cudaMemsetAsync(S->d_hit, 0xff, sizeof(int) * (size_t)K, st));   // -1
     CKS(cudaMemsetAsync(S->d_jsmall, 0, sizeof(int) * (size_t)K, st));
     if (N > 1) {
@@ -429,34 +444,33 @@ int tvl1_sample_matches_skip(tvl1_handle* H, const uint8_t* d_frame0, size_t pit
     }
     int* h_hit = S->h_ints;
     int* h_js = S->h_ints + K;
-    CKS(cudaMemcpyAsync(h_hit, S->d_hit, sizeof(int) * (size_t)K, cudaMemcpyDeviceToHost, st));
-    CKS(cudaMemcpyAsync(h_js, S->d_jsmall, sizeof(int) * (size_t)K, cudaMemcpyDeviceToHost, st));
+    if ((rc = copy_words(S->d_hit, h_hit, K, st)) || (rc = copy_words(S->d_jsmall, h_js, K, st))) return rc;
     CKS(cudaStreamSynchronize(st));
     std::vector<long long> origin;
     resolve_origins(N, K, h_hit, h_js, &origin);
 
     // 3. locate the origin-th set pixel (row by prefix sums, column on the device), sample
-    std::vector<int> rows((size_t)K), ranks((size_t)K);
+    int* rows = S->h_ints + 4 * (size_t)K;
+    int* ranks = S->h_ints + 5 * (size_t)K;
     for (int k = 0; k < K; k++) {
         const long long o = origin[(size_t)k];
         const size_t y = (size_t)(std::upper_bound(prefix.begin(), prefix.end(), o) - prefix.begin()) - 1;
-        rows[(size_t)k] = (int)y;
-        ranks[(size_t)k] = (int)(o - prefix[y]);
+        rows[k] = (int)y;
+        ranks[k] = (int)(o - prefix[y]);
     }
-    CKS(cudaMemcpyAsync(S->d_row, rows.data(), sizeof(int) * (size_t)K, cudaMemcpyHostToDevice, st));
-    CKS(cudaMemcpyAsync(S->d_rank, ranks.data(), sizeof(int) * (size_t)K, cudaMemcpyHostToDevice, st));
+    if ((rc = copy_words(rows, S->d_row, K, st)) || (rc = copy_words(ranks, S->d_rank, K, st))) return rc;
     PickArgs a;
     a.f0 = d_frame0; a.f1 = d_frame1; a.p0 = pitch0; a.p1 = pitch1;
     a.u = d_u; a.v = d_v; a.pf = pitch_flow / 4; a.w = width; a.h = height;
     a.roi0x = roi0_x; a.roi0y = roi0_y; a.roi1x = roi1_x; a.roi1y = roi1_y;
     a.inv_scale = (float)(1. / scale);   // float inv_scale = 1./scale  (src/optflow.cpp:528)
+    a.q_is_map = q_is_map != 0;
     a.n = K; a.row = S->d_row; a.rank = S->d_rank; a.out = S->d_out; a.pos = S->d_pos;
     k_pick_points<<<(K + 3) / 4, 128, 0, st>>>(a);
     CKS(cudaGetLastError());
     int* h_pos = S->h_ints + 2 * (size_t)K;
-    CKS(cudaMemcpyAsync(S->h_out, S->d_out, sizeof(double) * 4 * (size_t)K, cudaMemcpyDeviceToHost, st));
-    CKS(cudaMemcpyAsync(h_pos, S->d_pos, sizeof(int) * 2 * (size_t)K, cudaMemcpyDeviceToHost, st));
-    CKS(cudaStreamSynchronize(st));   // rows/ranks vectors must outlive the copies above
+    if ((rc = copy_words(S->d_out, S->h_out, 8 * K, st)) || (rc = copy_words(S->d_pos, h_pos, 2 * K, st))) return rc;
+    CKS(cudaStreamSynchronize(st));
     for (int k = 0; k < K; k++) {
         px[k] = S->h_out[0 * (size_t)K + k];
         py[k] = S->h_out[1 * (size_t)K + k];

@@ -156,6 +156,53 @@ int tvl1_sample_matches_skip(tvl1_handle* h, const uint8_t* d_frame0, size_t pit
                              double* px, double* py, double* qx, double* qy, double* w,
                              int* positions, int* n_out, long long* rand_used, void* stream);
 
+/* Same with the `features` branch of random_points (src/optflow.cpp:544-550): with q_is_map != 0 the planes
+ * hold a MAP (flow + coordinate grid, as solve_wrapper leaves them after a feature pre-alignment) and
+ * q = (map(pos) + roi1) * inv_scale, without the pos term. */
+int tvl1_sample_matches_ex(tvl1_handle* h, const uint8_t* d_frame0, size_t pitch0,
+                           const uint8_t* d_frame1, size_t pitch1,
+                           const float* d_u, const float* d_v, size_t pitch_flow,
+                           int width, int height, int roi0_x, int roi0_y, int roi1_x, int roi1_y,
+                           float scale, int npoints, long long seed, long long rand_skip, int q_is_map,
+                           double* px, double* py, double* qx, double* qy, double* w,
+                           int* positions, int* n_out, long long* rand_used, void* stream);
+
+/* ---- feature pre-alignment (N4): find_alignment, src/features.cpp:46-167, called by solve_rois whenever
+ * a job asks for `features`, has no roi, or pairs frames of different size (src/optflow.cpp:366-377).
+ * Keypoints + 256-bit binary descriptors on both frames (FAST-9 / Harris ranking / intensity-centroid
+ * orientation / steered BRIEF over an ORB-style pyramid), Hamming 2-NN + ratio test, RANSAC homography,
+ * the reference's +-20 % zoom sanity check; the top 2x3 of the homography is the affine that maps
+ * `moving` (the pair's frame1) coordinates to `fixed` (frame0) coordinates.  Identity when there are not
+ * more than 10 good matches or the check fails, as in the reference.  Not OpenCV's ORB bit for bit (its
+ * learned test pattern is part of OpenCV's source): tests compare transforms.  SURF (features type 2,
+ * the reference's default, non-free) takes the same path. */
+typedef struct tvl1_feature_params {
+    int nfeatures;          /* 5000   orb_defaults, src/features.cpp:19-32 */
+    float scale_factor;     /* 1.2 */
+    int nlevels;            /* 8 */
+    int edge_threshold;     /* 31 */
+    int first_level;        /* 0 (only 0) */
+    int patch_size;         /* 31 */
+    int fast_threshold;     /* 20 */
+    float ratio;            /* 0.8    src/features.cpp:107 */
+    double ransac;          /* 5.0    reprojection threshold, src/features.cpp:133 */
+    int homo;               /* 8 = cv::RANSAC (4, 16 are served by RANSAC too), 0 = least squares on all matches */
+    int debug;              /* prints the counts and the homography like the reference's debug mode */
+    int reserved[4];
+} tvl1_feature_params;
+void tvl1_default_feature_params(tvl1_feature_params* p);
+int tvl1_find_alignment(tvl1_handle* h, const uint8_t* d_moving, size_t pitch_moving, int w_moving, int h_moving,
+                        const uint8_t* d_fixed, size_t pitch_fixed, int w_fixed, int h_fixed,
+                        const tvl1_feature_params* prm, float* affine /* [6], row-major 2x3 */,
+                        int* n_matches, int* n_good, void* stream);
+/* cv::cuda::warpAffine(src, dst, affine, dsize, INTER_LINEAR, BORDER_CONSTANT, 0) of src/optflow.cpp:374
+ * (8-bit frame) and :431-432 (fp32 map planes), computed as cv::warpAffine does: dst(x) = src(A^-1 x),
+ * source coordinates in 1/32 px.  Pitches in bytes. */
+int tvl1_warp_affine_u8(const uint8_t* d_src, size_t spitch, int sw, int sh, const float* affine,
+                        uint8_t* d_dst, size_t dpitch, int dw, int dh, void* stream);
+int tvl1_warp_affine_f32(const float* d_src, size_t spitch, int sw, int sh, const float* affine,
+                         float* d_dst, size_t dpitch, int dw, int dh, void* stream);
+
 /* A stack of adjacent slices: pairs (k, k+1), k = 0 .. n_slices-2, solved in order on one GPU
  * (the pair loop of from_file, src/optflow.cpp:86-176, incl. its re-use of the previous pair's
  * q frame as the next p, :97-103).  Every slice is uploaded once; the upload of slice k+2 and
