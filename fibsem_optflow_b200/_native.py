@@ -366,8 +366,10 @@ class Solver:
         check(lib().tvl1_mask_flow_u8(self.handle, d_f1, pitch1, w, h, d_u, d_v, pitch_out, stream))
 
     def finish_flow_device(self, d_f1, pitch1, w, h, d_u, d_v, pitch_out, add_grid, stream=None):
-        """output_type "map": + coordinate grid; then flow = 0 where frame1 <= 1 (src/optflow.cpp:445-473)"""
-        check(lib().tvl1_finish_flow_u8(self.handle, d_f1, pitch1, w, h, d_u, d_v, pitch_out, int(bool(add_grid)), stream))
+        """output_type "map": + coordinate grid; then flow = 0 where frame1 <= 1 (src/optflow.cpp:445-473).
+        add_grid -1 subtracts the grid (the "flow" output of the features path, :434-438); d_f1 None: no mask."""
+        g = int(add_grid)
+        check(lib().tvl1_finish_flow_u8(self.handle, d_f1, pitch1, w, h, d_u, d_v, pitch_out, (g > 0) - (g < 0), stream))
 
     def find_alignment(self, moving, fixed, **kw):
         """find_alignment (src/features.cpp:46-167): host uint8 frames in, (affine 2x3 float32 mapping `moving`

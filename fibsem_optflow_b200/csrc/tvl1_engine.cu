@@ -953,14 +953,16 @@ int tvl1_finish_flow_u8(tvl1_handle* H, const uint8_t* d_frame1, size_t pitch1, 
                         float* d_u, float* d_v, size_t pitch_out, int add_grid, void* stream)
 {
     if (!H) return fail(TVL1_ERR_INVALID, "handle is null");
-    if (!d_frame1 || !d_u || !d_v || width <= 0 || height <= 0 || pitch_out % 4) return fail(TVL1_ERR_INVALID, "bad argument");
+    if (!d_u || !d_v || width <= 0 || height <= 0 || pitch_out % 4) return fail(TVL1_ERR_INVALID, "bad argument");
     CK(cudaSetDevice(H->device));
-    return launch_mask_flow(d_frame1, pitch1, width, height, d_u, d_v, pitch_out / 4, add_grid != 0, (cudaStream_t)stream);
+    return launch_mask_flow(d_frame1, pitch1, width, height, d_u, d_v, pitch_out / 4, add_grid > 0 ? 1 : (add_grid < 0 ? -1 : 0),
+                            (cudaStream_t)stream);
 }
 
 int tvl1_mask_flow_u8(tvl1_handle* H, const uint8_t* d_frame1, size_t pitch1, int width, int height,
                       float* d_u, float* d_v, size_t pitch_out, void* stream)
 {
+    if (!d_frame1) return fail(TVL1_ERR_INVALID, "frame1 is null");
     return tvl1_finish_flow_u8(H, d_frame1, pitch1, width, height, d_u, d_v, pitch_out, 0, stream);
 }
 

@@ -1,8 +1,8 @@
 // optflow_b200 -- job driver: the reference's `optflow <job.json[.gz]>` CLI on top of the C ABI.
 //
 // Mirrors main / from_file / get_rois / solve_rois / solve_wrapper / move_pm / upload_points of
-// the reference (src/optflow.cpp:29-178, 228-261, 302-392, 395-497, 574-641) for the
-// features == false path:
+// the reference (src/optflow.cpp:29-178, 228-261, 302-392, 395-497, 574-641), both the plain and the
+// feature pre-alignment path (N4: find_alignment of src/features.cpp:46-167 through tvl1_find_alignment):
 //   * same job JSON (comments tolerated, .gz transparently inflated), same key precedence
 //     im_args.get(key, args.get(key, default));
 //   * same pair loop incl. re-use of the previous pair's decoded frame (:97-103);
@@ -10,10 +10,11 @@
 //     alphabetical member order; same output naming
 //     <output_dir>/<output_name>_<scale %0.2f>[_top|_bottom]_{x,y}.tiff (:155-157, :345, :480-481);
 //   * output_type "map" | "flow" -> float TIFF planes, "random_points" -> match records.
+//   * "features" / no roi / frames of different size: frame1 is aligned to frame0 by keypoints and an
+//     affine warp before the solve, the map is warped by the same affine afterwards (:366-377, :411-444),
+//     and random_points takes its `features` branch (:544-550).  The descriptor is this library's own
+//     ORB-style one for either feature type (SURF is non-free): see tvl1_b200.h.
 // Differences, all because the dependency is out of scope or absent here:
-//   * no ORB/SURF pre-alignment (src/features.cpp): a job that asks for "features", or pairs of
-//     different size, are rejected; a pair without any ROI is solved on the whole frame
-//     without the alignment the reference would force (:366);
 //   * match batches are written to <output_dir>/point_matches_<n>.json with exactly the payload
 //     upload_points would PUT to the Render service (:620-634) -- there is no network here;
 // N2, the I/O path: frames are decoded on host threads into PINNED buffers `prefetch` pairs ahead; a
@@ -108,6 +109,8 @@ struct Driver {
     void *s_solve = nullptr, *s_copy = nullptr;   // streams
     FrameSlot slot[3];
     DeviceBuf raw, du, dv;
+    DeviceBuf mx, my;          // warped map planes of the features path
+    DeviceBuf aligned[2];      // frame1 after the affine pre-alignment (ping-pong: a second roi key re-aligns it)
     PinnedPool pool;
     std::vector<std::pair<void*, size_t>> in_copy;   // pinned buffers the copy stream may still read
     std::vector<std::future<bool>> writers;          // TIFF writers in flight
@@ -123,7 +126,7 @@ struct Driver {
         if (s_solve) { tvl1_stream_sync(s_solve); tvl1_stream_destroy(s_solve); }
         for (auto& b : in_copy) pool.put(b.first, b.second);
         if (solver) tvl1_destroy(solver);
-        for (DeviceBuf* f : {&slot[0].buf, &slot[1].buf, &slot[2].buf, &raw, &du, &dv})
+        for (DeviceBuf* f : {&slot[0].buf, &slot[1].buf, &slot[2].buf, &raw, &du, &dv, &mx, &my, &aligned[0], &aligned[1]})
             if (f->ptr) tvl1_dev_free(device, f->ptr);
     }
 };
@@ -241,9 +244,10 @@ void check_roi(const Rect& r, int w, int h, const char* which)
         pair_fail(std::string("roi outside the frame (") + which + ")");
 }
 
-// solve_wrapper (src/optflow.cpp:395-497), features == false.  f0 / f1: the pair's frames on the device.
+// solve_wrapper (src/optflow.cpp:395-497).  f0 / f1: the pair's frames on the device (f1 already moved by
+// `affine` when `features`).
 void solve_wrapper(Driver& D, const FrameSlot& f0, const FrameSlot& f1, const Rect& r0, const Rect& r1,
-                   Value& im, const Value& args)
+                   Value& im, const Value& args, const float* affine, bool features)
 {
     if (r0.w != r1.w || r0.h != r1.h) pair_fail("the two rois of a pair must have the same size");
     const int w = r0.w, h = r0.h;
@@ -256,9 +260,23 @@ void solve_wrapper(Driver& D, const FrameSlot& f0, const FrameSlot& f1, const Re
     ck(tvl1_calc_u8(D.solver, p0, (size_t)f0.w, p1, (size_t)f1.w, w, h, du, dv, (size_t)w * 4, D.s_solve, nullptr), "tvl1_calc_u8");
 
     const std::string output_type = pick(im, args, "output_type", Value("map")).asString();
-    // the coordinate grid of "map" (:445-466) and the frame1 <= 1 mask (:471-473), on the device
-    ck(tvl1_finish_flow_u8(D.solver, p1, (size_t)f1.w, w, h, du, dv, (size_t)w * 4, output_type == "map", D.s_solve),
-       "tvl1_finish_flow_u8");
+    if (features) {
+        // :411-444: map = flow + grid, moved by the SAME affine (cv::cuda::warpAffine, linear, constant 0),
+        // back to a displacement for "flow"; then the frame1 <= 1 mask (:471-473).  All on the device.
+        reserve(D, D.mx, (size_t)w * h * 4);
+        reserve(D, D.my, (size_t)w * h * 4);
+        float *mx = (float*)D.mx.ptr, *my = (float*)D.my.ptr;
+        ck(tvl1_finish_flow_u8(D.solver, nullptr, 0, w, h, du, dv, (size_t)w * 4, 1, D.s_solve), "map grid");
+        ck(tvl1_warp_affine_f32(du, (size_t)w * 4, w, h, affine, mx, (size_t)w * 4, w, h, D.s_solve), "tvl1_warp_affine_f32");
+        ck(tvl1_warp_affine_f32(dv, (size_t)w * 4, w, h, affine, my, (size_t)w * 4, w, h, D.s_solve), "tvl1_warp_affine_f32");
+        ck(tvl1_finish_flow_u8(D.solver, p1, (size_t)f1.w, w, h, mx, my, (size_t)w * 4, output_type == "flow" ? -1 : 0, D.s_solve),
+           "tvl1_finish_flow_u8");
+        du = mx; dv = my;
+    } else {
+        // the coordinate grid of "map" (:445-466) and the frame1 <= 1 mask (:471-473), on the device
+        ck(tvl1_finish_flow_u8(D.solver, p1, (size_t)f1.w, w, h, du, dv, (size_t)w * 4, output_type == "map", D.s_solve),
+           "tvl1_finish_flow_u8");
+    }
     if (output_type == "random_points") {
         const bool debug = args.get("debug", Value(false)).asBool();
         const float scale = pick(im, args, "scale", Value(0.5)).asFloat();
@@ -269,9 +287,9 @@ void solve_wrapper(Driver& D, const FrameSlot& f0, const FrameSlot& f1, const Re
         long long used = 0;
         // srand(time(0)) unless debug (:532-535); debug keeps drawing from one unseeded stream
         const long long seed = debug ? -1 : (long long)std::time(nullptr);
-        ck(tvl1_sample_matches_skip(D.solver, p0, (size_t)f0.w, p1, (size_t)f1.w, du, dv, (size_t)w * 4, w, h, r0.x, r0.y,
-                                    r1.x, r1.y, scale, npoints, seed, debug ? D.rand_skip : 0, px.data(), py.data(),
-                                    qx.data(), qy.data(), wt.data(), nullptr, &n, &used, D.s_solve), "tvl1_sample_matches");
+        ck(tvl1_sample_matches_ex(D.solver, p0, (size_t)f0.w, p1, (size_t)f1.w, du, dv, (size_t)w * 4, w, h, r0.x, r0.y,
+                                  r1.x, r1.y, scale, npoints, seed, debug ? D.rand_skip : 0, features ? 1 : 0, px.data(),
+                                  py.data(), qx.data(), qy.data(), wt.data(), nullptr, &n, &used, D.s_solve), "tvl1_sample_matches");
         if (debug) D.rand_skip += used;
         Value& pm = im["point_matches"];
         if (!pm.isMember("p")) {
@@ -413,31 +431,71 @@ void stage_frame(Driver& D, FrameSlot& sl, const std::string& name, float scale,
     sl.name = name; sl.scale = scale; sl.w = dw; sl.h = dh;
 }
 
+// orb_defaults (src/features.cpp:19-32) + ratio / ransac / homo (:107, :133), per-pair > global > default
+tvl1_feature_params feature_params(const Value& im, const Value& args)
+{
+    tvl1_feature_params p;
+    tvl1_default_feature_params(&p);
+    p.nfeatures = (int)pick(im, args, "nfeatures", Value(5000)).asInt();
+    p.scale_factor = pick(im, args, "scaleFactor", Value(1.2)).asFloat();
+    p.nlevels = (int)pick(im, args, "nlevels", Value(8)).asInt();
+    p.edge_threshold = (int)pick(im, args, "edgeThreshold", Value(31)).asInt();
+    p.first_level = (int)pick(im, args, "firstLevel", Value(0)).asInt();
+    p.patch_size = (int)pick(im, args, "patchSize", Value(31)).asInt();
+    p.fast_threshold = (int)pick(im, args, "fastThreshold", Value(20)).asInt();
+    p.ratio = pick(im, args, "ratio", Value(0.8)).asFloat();
+    p.ransac = pick(im, args, "ransac", Value(5.0)).asDouble();
+    p.homo = (int)pick(im, args, "homo", Value(8)).asInt();
+    p.debug = args.get("debug", Value(false)).asBool() ? 1 : 0;
+    return p;
+}
+
 // solve_rois (src/optflow.cpp:312-392)
-void solve_rois(Driver& D, const FrameSlot& f0, const FrameSlot& f1, const Value& rois, Value& im, Value& args)
+void solve_rois(Driver& D, const FrameSlot& f0, const FrameSlot& f1_in, const Value& rois, Value& im, Value& args)
 {
     // src/optflow.cpp:323-338: an explicit false at either level wins, then a true at either level
-    bool want_features;
-    if (im.isMember("features") && !im.at("features").asBool()) want_features = false;
-    else if (args.isMember("features") && !args.at("features").asBool()) want_features = false;
-    else want_features = im.get("features", Value(false)).asBool() || args.get("features", Value(false)).asBool();
-    if (want_features) pair_fail("\"features\" (ORB/SURF pre-alignment) is not part of this build");
+    bool features;
+    if (im.isMember("features") && !im.at("features").asBool()) features = false;
+    else if (args.isMember("features") && !args.at("features").asBool()) features = false;
+    else features = im.get("features", Value(false)).asBool() || args.get("features", Value(false)).asBool();
     ck(tvl1_stream_wait(D.s_solve, D.s_copy), "stream wait");   // both frames have arrived and are prescaled
+    FrameSlot f1 = f1_in;   // a view: replaced by the aligned frame below, the slot itself stays as decoded
+    float affine[6] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f};
+    int flip = 0;
     for (const auto& kv : *rois.o) {   // alphabetical, like Json::Value::getMemberNames()
         const std::string& key = kv.first;
         im["output_suffix"] = (key == "top" || key == "bottom") ? Value("_" + key) : Value("");
         if (key == "custom_diff") {
+            if (features) std::cerr << "Features isn't compatible with different ROIs for each image.\n Ignoring features.\n";
             const Rect r0 = roi_from_array(kv.second.at("0")), r1 = roi_from_array(kv.second.at("1"));
             check_roi(r0, f0.w, f0.h, "custom 0");
             check_roi(r1, f1.w, f1.h, "custom 1");
-            solve_wrapper(D, f0, f1, r0, r1, im, args);
+            // the reference hands `features` through as is (:363): the map is still moved by whatever
+            // `affine` holds (identity unless an earlier roi key of this pair aligned)
+            solve_wrapper(D, f0, f1, r0, r1, im, args, affine, features);
         } else {
-            if (f0.w != f1.w || f0.h != f1.h) pair_fail("frames of different size need the feature pre-alignment, which is not part of this build");
-            if (key == "default")
-                std::cerr << "note: no roi given; the reference would pre-align with features here, this build solves the whole frame as is\n";
+            const bool differ = f0.w != f1.w || f0.h != f1.h;
+            if (features || differ || key == "default") {
+                if (differ || (key == "default" && !features))
+                    std::cerr << "Rows or columns differ between frames no ROI selected, reverting to features even though it wasn't selected.\n";
+                // :373-376: frame1 is replaced by its aligned version for this and every later roi key of
+                // the pair (a later key aligns the already aligned frame again, as the reference does)
+                const tvl1_feature_params fp = feature_params(im, args);
+                int nm = 0, ng = 0;
+                ensure_solver(D, tv_params(im, args));
+                ck(tvl1_find_alignment(D.solver, (const uint8_t*)f1.buf.ptr, (size_t)f1.w, f1.w, f1.h, (const uint8_t*)f0.buf.ptr, (size_t)f0.w,
+                                       f0.w, f0.h, &fp, affine, &nm, &ng, D.s_solve), "tvl1_find_alignment");
+                DeviceBuf& dst = D.aligned[flip];
+                flip ^= 1;
+                reserve(D, dst, (size_t)f0.w * f0.h);
+                ck(tvl1_warp_affine_u8((const uint8_t*)f1.buf.ptr, (size_t)f1.w, f1.w, f1.h, affine, (uint8_t*)dst.ptr, (size_t)f0.w,
+                                       f0.w, f0.h, D.s_solve), "tvl1_warp_affine_u8");
+                f1.buf = dst; f1.w = f0.w; f1.h = f0.h;
+                features = true;
+            }
             const Rect r = roi_from_array(kv.second);
             check_roi(r, f0.w, f0.h, key.c_str());
-            solve_wrapper(D, f0, f1, r, r, im, args);
+            solve_wrapper(D, f0, f1, r, r, im, args, affine, features);
         }
     }
     if (pick(im, args, "output_type", Value("map")).asString() == "random_points") move_pm(im, args);

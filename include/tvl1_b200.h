@@ -122,7 +122,8 @@ int tvl1_mask_flow_u8(tvl1_handle* h, const uint8_t* d_frame1, size_t pitch1, in
 /* The post-processing of solve_wrapper in one pass (src/optflow.cpp:445-473): with add_grid != 0
  * ("output_type": "map") the coordinate grid is added to the flow, u += x, v += y -- the reference
  * builds that grid in a host double loop and uploads it (:451-465) --, then flow = 0 where
- * frame1 <= 1 (:471-473).  add_grid == 0 is tvl1_mask_flow_u8. */
+ * frame1 <= 1 (:471-473).  add_grid == 0 is tvl1_mask_flow_u8; add_grid < 0 SUBTRACTS the grid (the "flow"
+ * output after a feature pre-alignment, :434-438); d_frame1 == NULL skips the mask. */
 int tvl1_finish_flow_u8(tvl1_handle* h, const uint8_t* d_frame1, size_t pitch1, int width,
                         int height, float* d_u, float* d_v, size_t pitch_out, int add_grid,
                         void* stream);

@@ -150,7 +150,9 @@ def test_general_scale_and_prefetch(gpu, orc, tmp_path):
         write_png(p, a)
         names.append(p)
     pairs = [(0, 1), (2, 3), (4, 5)]
+    # a whole-frame "custom" roi: without any roi the reference pre-aligns by features (src/optflow.cpp:366)
     job = {"debug": True, "output_type": "flow", "scale": 0.3, "lambda": 0.15, "nscales": 3, "output_dir": str(tmp_path),
+           "rois": {"custom": [0, 0, 78, 60]},
            "images": [{"p": names[a], "q": names[b], "output_name": "p%d" % a} for a, b in pairs]}
     jf = str(tmp_path / "job.json")
     json.dump(job, open(jf, "w"))
@@ -197,3 +199,41 @@ def test_sharded_random_points_cover_every_pair(gpu, tmp_path):
     json.dump(job, open(jf, "w"))
     subprocess.check_call([exe, jf], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     assert [g["pId"] for g in json.load(open(job["matches_file"]))] == ["h0", "h1", "h2", "h4"]
+
+
+def test_job_without_roi_is_prealigned(gpu, tmp_path):
+    """N4: a pair without any roi is aligned by features first (src/optflow.cpp:366-377), its map moved by
+    the same affine (:411-444), and its matches take the `features` branch of random_points (:544-550).
+    The driver and the Python mirror run the same library: bit-equal planes and records."""
+    import cv2
+    from fibsem_optflow_b200 import api
+    exe = build_cli()
+    h, w, m = 420, 560, 60
+    c = synth.to_u8(synth.texture(h + 2 * m, w + 2 * m, 3, 2.0, coarse=8))
+    f0 = np.ascontiguousarray(c[m:m + h, m:m + w])
+    M = np.array([[1.01, -0.006, 4.2 + m], [0.006, 1.01, -2.7 + m]])
+    f1 = cv2.warpAffine(c, M, (w, h), flags=cv2.INTER_CUBIC | cv2.WARP_INVERSE_MAP)
+    n0, n1 = str(tmp_path / "f0.png"), str(tmp_path / "f1.png")
+    write_png(n0, f0)
+    write_png(n1, f1)
+    common = {"debug": True, "scale": 1.0, "lambda": 0.15, "nscales": 3, "npoints": 5, "output_dir": str(tmp_path)}
+    job = dict(common, images=[
+        {"p": n0, "q": n1, "output_name": "m", "output_type": "map"},
+        {"p": n0, "q": n1, "output_name": "f", "output_type": "flow", "features": 1, "rois": {"top": 80}},
+        {"p": n0, "q": n1, "output_type": "random_points", "pId": "a", "qId": "b", "pGroupId": "1.0", "qGroupId": "2.0"}])
+    jf = str(tmp_path / "job.json")
+    json.dump(job, open(jf, "w"))
+    subprocess.check_call([exe, jf], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    args = dict(common)
+    want = api.solve_rois(f0, f1, {"default": [0, 0, w, h]}, {"output_type": "map"}, args)["default"]
+    assert np.array_equal(read_tiff_f32(str(tmp_path / "m_1.00_x.tiff")), want[0])
+    assert np.array_equal(read_tiff_f32(str(tmp_path / "m_1.00_y.tiff")), want[1])
+    assert abs(np.median(want[0] - np.arange(w, dtype=np.float32)[None, :]) + 4.2) < 1.5
+    want = api.solve_rois(f0, f1, {"top": [0, 0, w, 80]}, {"output_type": "flow", "features": 1}, args)["top"]
+    assert np.array_equal(read_tiff_f32(str(tmp_path / "f_1.00_top_x.tiff")), want[0])
+    assert np.array_equal(read_tiff_f32(str(tmp_path / "f_1.00_top_y.tiff")), want[1])
+    im = {"output_type": "random_points", "pId": "a", "qId": "b", "pGroupId": "1.0", "qGroupId": "2.0"}
+    api.solve_rois(f0, f1, {"default": [0, 0, w, h]}, im, args, seed=-1)
+    got = json.load(open(str(tmp_path / "point_matches_000.json")))
+    assert got == args["point_matches"]
+    api.release_solvers()
