@@ -46,8 +46,12 @@ CPU_CROP = 2048          # the CPU legs run a CPU_CROP^2 crop of the pair (bound
 
 
 def workload(args):
-    return {"workload": "configs[1]: single %dx%d 8-bit slice pair, %d scales, %d warps" % (
-                args.size, args.size, args.scales, args.warps),
+    tag = {2048: "configs[0]", 8192: "configs[1]", 16384: "configs[3] (cross-section pair, large displacement)"}.get(
+        args.size, "configs[1]-style")
+    return {"workload": "%s: single %dx%d 8-bit slice pair, %d scales, %d warps" % (
+                tag, args.size, args.size, args.scales, args.warps),
+            "synthetic": {"shift_px": [args.dx, args.dy], "shear_px_over_height": args.shear_px, "seed": args.seed,
+                          "texture_coarse": args.coarse},
             "width": args.size, "height": args.size, "nscales": args.scales, "warps": args.warps,
             "tau": 0.25, "lambda": 0.15, "theta": 0.3, "epsilon": 0.01, "scaleStep": 0.8,
             "innerIterations": 30, "outerIterations": 10, "medianFiltering": 5,
@@ -60,8 +64,8 @@ def workload(args):
 
 
 def make_pair(args, rank):
-    return synth.make_pair(args.size, args.size, seed=7 + rank, dx=1.3, dy=-0.7,
-                           shear=4.0 / args.size)
+    return synth.make_pair(args.size, args.size, seed=args.seed + rank, dx=args.dx, dy=args.dy,
+                           shear=args.shear_px / args.size, margin=args.margin, coarse=args.coarse)
 
 
 class ClockSampler(threading.Thread):
@@ -504,6 +508,12 @@ def main():
     ap.add_argument("--size", type=int, default=8192)
     ap.add_argument("--scales", type=int, default=6)
     ap.add_argument("--warps", type=int, default=5)
+    ap.add_argument("--dx", type=float, default=1.3, help="synthetic shift of the pair (configs[3]: 8-20 px)")
+    ap.add_argument("--dy", type=float, default=-0.7)
+    ap.add_argument("--shear-px", type=float, default=4.0, help="shear over the frame height, px")
+    ap.add_argument("--seed", type=int, default=7)
+    ap.add_argument("--margin", type=int, default=32)
+    ap.add_argument("--coarse", type=int, default=0, help="extra coarse texture component (configs[3]: 16)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-parity", action="store_true", help="skip the parity leg (configs[0] vs the oracle)")
     ap.add_argument("--stack-pairs", type=int, default=512, help="configs[2] leg: pairs of the whole stack, split over the GPUs (0 = off)")
