@@ -210,11 +210,11 @@ static int resident_blocks(int which)
     cudaError_t e;
     if (which == KI_FUSED) {
         // the shared-memory ring needs the opt-in limit raised first
-        cudaFuncSetAttribute(k_iterate2<ITER_NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, TVL1_FUSED_BYTES(ITER_NW));
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_iterate2<ITER_NW>, 32 * ITER_NW, TVL1_FUSED_BYTES(ITER_NW));
+        cudaFuncSetAttribute(k_iterate2<ITER_NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, TVL1_RING_BYTES(ITER_NW));
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_iterate2<ITER_NW>, 32 * ITER_NW, TVL1_RING_BYTES(ITER_NW));
     } else if (which == KI_OUTER) {
-        cudaFuncSetAttribute(k_outer<ITER_NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, TVL1_FUSED_BYTES(ITER_NW));
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_outer<ITER_NW>, 32 * ITER_NW, TVL1_FUSED_BYTES(ITER_NW));
+        cudaFuncSetAttribute(k_outer<ITER_NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, TVL1_RING_BYTES(ITER_NW));
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_outer<ITER_NW>, 32 * ITER_NW, TVL1_RING_BYTES(ITER_NW));
     } else if (which == KI_MULTI) {
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_iterate_multi<ITER_NW, 4>, 32 * ITER_NW, 0);
     } else if (which == KI_LARGE) {
@@ -240,11 +240,10 @@ size_t iterate_max_blocks()
 // Rows per tile and grid size.  A tile is one warp's strip x R rows and every resident warp walks
 // the tile list with a grid stride: tall tiles amortise the halo rows (R / (R + halo)), but the
 // tile count has to spread evenly over the resident warps (no nearly empty last round).
-static int tile_rows_search(int w, int h, int strip, int halo, int rmin, int resident_blocks, int* grid, int units)
+static int tile_rows_search(int w, int h, int strip, int halo, int rmin, int resident_blocks, int* grid)
 {
-    // units: tile walkers per block (warps; warp PAIRS for the warp-specialised two-iteration pass)
     const long long ns = cdiv(w, strip);
-    const long long slots = (long long)resident_blocks * units;
+    const long long slots = (long long)resident_blocks * ITER_NW;
     double best = -1.0;
     int best_r = rmin;
     long long best_g = 1;
@@ -266,22 +265,22 @@ static int tile_rows_search(int w, int h, int strip, int halo, int rmin, int res
     static const bool verbose = getenv("TVL1_DEV_VERBOSE") != nullptr;
     if (verbose)
         fprintf(stderr, "tile_rows %dx%d strip %d: R=%d warps=%lld tiles=%lld\n", w, h, strip, best_r, best_g, ns * cdiv(h, best_r));
-    *grid = (int)((best_g + units - 1) / units);
+    *grid = (int)((best_g + ITER_NW - 1) / ITER_NW);
     return best_r;
 }
 
 // the search runs once per (size, kernel): a solve launches the same few shapes hundreds of times
-static int tile_rows(int w, int h, int strip, int halo, int rmin, int resident_blocks, int* grid, int units = ITER_NW)
+static int tile_rows(int w, int h, int strip, int halo, int rmin, int resident_blocks, int* grid)
 {
-    struct Entry { int w, h, strip, resident, units, rows, grid; };
+    struct Entry { int w, h, strip, resident, rows, grid; };
     static thread_local Entry cache[32];
     static thread_local int used = 0, next = 0;
     for (int i = 0; i < used; i++) {
         const Entry& e = cache[i];
-        if (e.w == w && e.h == h && e.strip == strip && e.resident == resident_blocks && e.units == units) { *grid = e.grid; return e.rows; }
+        if (e.w == w && e.h == h && e.strip == strip && e.resident == resident_blocks) { *grid = e.grid; return e.rows; }
     }
-    Entry e = {w, h, strip, resident_blocks, units, 0, 0};
-    e.rows = tile_rows_search(w, h, strip, halo, rmin, resident_blocks, &e.grid, units);
+    Entry e = {w, h, strip, resident_blocks, 0, 0};
+    e.rows = tile_rows_search(w, h, strip, halo, rmin, resident_blocks, &e.grid);
     cache[next] = e;
     next = (next + 1) % 32;
     if (used < 32) used++;
@@ -329,25 +328,24 @@ int launch_outer(IterArgs& a, cudaStream_t st)
 {
     int grid = 1, g1 = 1;
     const int resident = resident_blocks(KI_OUTER);
-    const int FU = ITER_NW / TVL1_FUSED_TILE_WARPS;   // tile walkers per block of the two-iteration pass
-    const long long slots = (long long)resident * ITER_NW, slots2 = (long long)resident * FU;
+    const long long slots = (long long)resident * ITER_NW;
     const long long ns2 = cdiv(a.w, TVL1_STRIP2), ns1 = cdiv(a.w, TVL1_STRIP);
     int R2 = 0, R1 = 0;
     // small levels are bound by latency: the shortest tiles that still give every tile its own warp
     for (int r = 1; r <= 8 && !R2; ++r)
-        if (ns2 * cdiv(a.h, r) <= slots2) R2 = r;
+        if (ns2 * cdiv(a.h, r) <= slots) R2 = r;
     for (int r = 1; r <= 8 && !R1; ++r)
         if (ns1 * cdiv(a.h, r) <= slots) R1 = r;
     if (R2) {
         a.rows = R2;
-        grid = (int)((ns2 * cdiv(a.h, R2) + FU - 1) / FU);
+        grid = (int)((ns2 * cdiv(a.h, R2) + ITER_NW - 1) / ITER_NW);
     } else {
-        a.rows = tile_rows(a.w, a.h, TVL1_STRIP2, 3, 8, resident, &grid, FU);
+        a.rows = tile_rows(a.w, a.h, TVL1_STRIP2, 3, 8, resident, &grid);
     }
     a.rows1 = R1 ? R1 : tile_rows(a.w, a.h, TVL1_STRIP, 1, 4, resident, &g1);   // single passes stride over the same grid
     dim3 b(32, ITER_NW), g(grid);
     void* args[] = {(void*)&a};
-    cudaError_t e = cudaLaunchCooperativeKernel((const void*)k_outer<ITER_NW>, g, b, args, TVL1_FUSED_BYTES(ITER_NW), st);
+    cudaError_t e = cudaLaunchCooperativeKernel((const void*)k_outer<ITER_NW>, g, b, args, TVL1_RING_BYTES(ITER_NW), st);
     if (e != cudaSuccess) return fail(TVL1_ERR_CUDA, "cooperative launch of k_outer failed: %s", cudaGetErrorString(e));
     return TVL1_OK;
 }
@@ -355,9 +353,9 @@ int launch_outer(IterArgs& a, cudaStream_t st)
 int launch_iterate2(IterArgs& a, cudaStream_t st)
 {
     int grid = 1;
-    a.rows = tile_rows(a.w, a.h, TVL1_STRIP2, 3, 8, resident_blocks(KI_FUSED), &grid, ITER_NW / TVL1_FUSED_TILE_WARPS);   // 3 halo rows per tile
+    a.rows = tile_rows(a.w, a.h, TVL1_STRIP2, 3, 8, resident_blocks(KI_FUSED), &grid);   // 3 halo rows per tile
     dim3 b(32, ITER_NW);
-    k_iterate2<ITER_NW><<<grid, b, TVL1_FUSED_BYTES(ITER_NW), st>>>(a);
+    k_iterate2<ITER_NW><<<grid, b, TVL1_RING_BYTES(ITER_NW), st>>>(a);
     CK(cudaGetLastError());
     return TVL1_OK;
 }
