@@ -556,6 +556,7 @@ static int check_params(const tvl1_params* p)
     if (p->median_filtering != 1 && p->median_filtering != 5)
         return fail(TVL1_ERR_UNSUPPORTED, "medianFiltering must be 1 or 5");
     if (!(p->theta > 0.0)) return fail(TVL1_ERR_INVALID, "theta must be > 0");
+    if (!(p->lambda >= 0.0)) return fail(TVL1_ERR_INVALID, "lambda must be >= 0");   // the threshold step assumes l_t * grad >= 0
     return TVL1_OK;
 }
 
