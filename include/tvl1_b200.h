@@ -16,6 +16,18 @@
  *                                          random_points src/optflow.h:33,
  *                                          src/optflow.cpp:522-572
  *
+ *   tvl1_finish_flow_u8                 <- map grid + mask of solve_wrapper   src/optflow.cpp:445-473
+ *   tvl1_find_alignment                 <- find_alignment   src/features.cpp:46-167
+ *   tvl1_warp_affine_u8 / _f32          <- cv::cuda::warpAffine   src/optflow.cpp:374, 431-432
+ *   tvl1_prescale_u8                    <- the loader's cv::resize   src/optflow.cpp:111,124
+ *   tvl1_stack_run                      <- the pair loop of from_file   src/optflow.cpp:75-178
+ *
+ * NUMERICS: the solver computes what OpenCV's CPU class cv::DualTVL1OpticalFlow computes (cubic
+ * 1/32-px remap, 5x5 median per outer iteration, stop test every iteration), bit for bit against
+ * the CPU restatement in oracle/.  The reference BINARY calls cv::cuda::OpticalFlowDual_TVL1
+ * (src/optflow.cpp:518: flat loop, no median, another bicubic, fast-math), so outputs are not
+ * bit-comparable with that binary's for the same job; see DESIGN.md section 1.
+ *
  * Conventions: plain pointers and sizes, no C++ or torch types.  "d_" pointers are
  * device memory on the handle's device, "h_" pointers are host memory.  8-bit images
  * are single channel rows with a byte pitch (the reference passes GpuMat ROI views,
