@@ -109,6 +109,47 @@ int make_plane_map(CUtensorMap* tm, const float* base, int pitch, int h, int box
     return TVL1_OK;
 }
 
+// n fp32 planes {pitch x h} at equal distances as a 3-D tensor {x, y, plane}; the box is one 128-px row of every plane
+static int make_section_map(CUtensorMap* tm, const float* base, int pitch, int h, int n, size_t plane_stride_bytes)
+{
+    EncodeTiledFn enc = tensor_map_encoder();
+    if (!enc) return fail(TVL1_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t dims[3] = {(cuuint64_t)pitch, (cuuint64_t)h, (cuuint64_t)n};
+    const cuuint64_t strides[2] = {(cuuint64_t)pitch * sizeof(float), (cuuint64_t)plane_stride_bytes};
+    const cuuint32_t box[3] = {128u, 1u, (cuuint32_t)n}, es[3] = {1, 1, 1};
+    const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, es,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return fail(TVL1_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for %d planes of %dx%d", (int)r, n, pitch, h);
+    return TVL1_OK;
+}
+
+// the tensor maps the two-iteration pass fills its ring through (IterMaps), from the plane pointers of `a`:
+// the planes of each section must sit at equal, 16-byte aligned distances
+static int make_section(CUtensorMap* tm, const float* const* planes, int n, int pitch, int h)
+{
+    const ptrdiff_t d = (const char*)planes[1] - (const char*)planes[0];
+    bool even = d > 0 && d % 16 == 0 && (size_t)d >= (size_t)pitch * h * sizeof(float) && !((uintptr_t)planes[0] & 15);
+    for (int k = 2; k < n && even; k++) even = (const char*)planes[k] - (const char*)planes[k - 1] == d;
+    if (!even) return fail(TVL1_ERR_INVALID, "the planes of a ring section must sit at equal 16-byte aligned distances");
+    return make_section_map(tm, planes[0], pitch, h, n, (size_t)d);
+}
+
+int make_iter_maps(IterArgs& a)
+{
+    int rc;
+    const float* c[3] = {a.I1wx, a.I1wy, a.rho_c};
+    if ((rc = make_section(&a.tm.c, c, 3, a.pitch, a.h))) return rc;
+    for (int t = 0; t < 2; t++) {
+        const float* u[2] = {a.u1[t], a.u2[t]};
+        const float* p[4] = {a.p11[t], a.p12[t], a.p21[t], a.p22[t]};
+        if ((rc = make_section(&a.tm.u[t], u, 2, a.pitch, a.h))) return rc;
+        if ((rc = make_section(&a.tm.p[t], p, 4, a.pitch, a.h))) return rc;
+    }
+    return TVL1_OK;
+}
+
 // ---------------------------------------------------------------- pyramid geometry (A.2)
 
 static int scaled_size(int n, double f) { return (int)lrint((double)n * f); }   // round half even
@@ -385,6 +426,7 @@ int launch_median(const MedianArgs& a, int planes, cudaStream_t st)
 struct Level {
     alignas(64) CUtensorMap tm_med[2][2];   // median tiles of [u1 | u2][twin] (built with the arena)
     CUtensorMap tm_I1[2];                   // warp windows of I1: RW x 16 and RW x RH boxes
+    IterMaps tm_iter;                       // ring rows of the two-iteration pass
     int w, h, pitch;
     float *I0, *I1, *u1, *u2;   // u1/u2: buffer [0] of the twin pair; [1] is shared scratch
 };
@@ -520,6 +562,16 @@ static int ensure_capacity(tvl1_handle* H, int w, int h, cudaStream_t st)
             const int r = make_plane_map(&lv.tm_I1[k], lv.I1, lv.pitch, lv.h, TVL1_WP_RW, k == 0 ? 16 : TVL1_WP_RH);
             if (r) { release_arena(H); return r; }
         }
+        {
+            IterArgs ia;
+            ia.I1wx = H->I1wx; ia.I1wy = H->I1wy; ia.rho_c = H->rho;
+            ia.u1[0] = lv.u1; ia.u1[1] = H->u1x; ia.u2[0] = lv.u2; ia.u2[1] = H->u2x;
+            for (int k = 0; k < 2; k++) { ia.p11[k] = H->p[0][k]; ia.p12[k] = H->p[1][k]; ia.p21[k] = H->p[2][k]; ia.p22[k] = H->p[3][k]; }
+            ia.w = lv.w; ia.h = lv.h; ia.pitch = lv.pitch;
+            const int r = make_iter_maps(ia);
+            if (r) { release_arena(H); return r; }
+            lv.tm_iter = ia.tm;
+        }
     }
     H->cap_w = w; H->cap_h = h; H->cap_scales = H->prm.nscales; H->cap_step = H->prm.scale_step;
     // pad columns are read (never used) by the vectorised kernels: give them defined contents.  On the
@@ -640,6 +692,7 @@ static int calc_device(tvl1_handle* H, const uint8_t* f0, size_t pitch0, const u
         ia.l_t = l_t; ia.theta = theta; ia.taut = taut; ia.scaled_eps = scaled_eps; ia.one = 1.0f;
         ia.level = s; ia.ctrl = H->d_ctrl; ia.partials = H->d_partials; ia.errlog = nullptr;
         ia.mode = 0; ia.inner_max = H->inner;
+        ia.tm = lv.tm_iter;
         const bool fused = (long long)lv.w * lv.h >= H->fused_min_px && H->inner >= 2;
         const bool multi = !fused && H->multi_iter && H->inner >= 2;
         MedianArgs ma;
@@ -1197,19 +1250,35 @@ static int k_iterate_impl(int fused, const float* d_I1wx, const float* d_I1wy, c
     const size_t pb = (size_t)pitch * h * sizeof(float);
     const size_t nb = iterate_max_blocks();
     char* tmp = nullptr;
-    const size_t ctrl_off = 6 * pb, part_off = ctrl_off + 1024 * ((sizeof(Ctrl) + 1023) / 1024);
+    // the two-iteration pass fills its ring by bulk tensor copies of whole sections (IterMaps): its operands are
+    // staged as 15 equally spaced planes {I1wx, I1wy, rho_c | u1, u2 | u1', u2' | p11..p22 | p11'..p22'}; the
+    // one-iteration kernel works on the caller's planes with 6 twins
+    const int nplanes = fused ? 15 : 6;
+    const size_t ctrl_off = nplanes * pb, part_off = ctrl_off + 1024 * ((sizeof(Ctrl) + 1023) / 1024);
     const size_t log_off = part_off + nb * sizeof(double);
     const size_t total = log_off + (size_t)(n + 1) * sizeof(double);
     CK(cudaMalloc(&tmp, total));
     cudaError_t e = cudaMemsetAsync(tmp, 0, total, st);
     if (e != cudaSuccess) { cudaFree(tmp); return fail(TVL1_ERR_CUDA, "memset: %s", cudaGetErrorString(e)); }
-    float* tw[6];
-    for (int k = 0; k < 6; k++) tw[k] = (float*)(tmp + k * pb);
+    float* tw[15];
+    for (int k = 0; k < nplanes; k++) tw[k] = (float*)(tmp + k * pb);
+    float* const user[6] = {d_u1, d_u2, d_p11, d_p12, d_p21, d_p22};
     IterArgs a;
-    a.I1wx = d_I1wx; a.I1wy = d_I1wy; a.rho_c = d_rho_c;   // grad is recomputed in the kernel
-    a.u1[0] = d_u1; a.u1[1] = tw[0]; a.u2[0] = d_u2; a.u2[1] = tw[1];
-    a.p11[0] = d_p11; a.p11[1] = tw[2]; a.p12[0] = d_p12; a.p12[1] = tw[3];
-    a.p21[0] = d_p21; a.p21[1] = tw[4]; a.p22[0] = d_p22; a.p22[1] = tw[5];
+    if (fused) {
+        const float* cs[3] = {d_I1wx, d_I1wy, d_rho_c};
+        for (int k = 0; k < 3; k++) cudaMemcpyAsync(tw[k], cs[k], pb, cudaMemcpyDeviceToDevice, st);
+        for (int k = 0; k < 2; k++) cudaMemcpyAsync(tw[3 + k], user[k], pb, cudaMemcpyDeviceToDevice, st);
+        for (int k = 0; k < 4; k++) cudaMemcpyAsync(tw[7 + k], user[2 + k], pb, cudaMemcpyDeviceToDevice, st);
+        a.I1wx = tw[0]; a.I1wy = tw[1]; a.rho_c = tw[2];
+        a.u1[0] = tw[3]; a.u2[0] = tw[4]; a.u1[1] = tw[5]; a.u2[1] = tw[6];
+        a.p11[0] = tw[7]; a.p12[0] = tw[8]; a.p21[0] = tw[9]; a.p22[0] = tw[10];
+        a.p11[1] = tw[11]; a.p12[1] = tw[12]; a.p21[1] = tw[13]; a.p22[1] = tw[14];
+    } else {
+        a.I1wx = d_I1wx; a.I1wy = d_I1wy; a.rho_c = d_rho_c;   // grad is recomputed in the kernel
+        a.u1[0] = d_u1; a.u1[1] = tw[0]; a.u2[0] = d_u2; a.u2[1] = tw[1];
+        a.p11[0] = d_p11; a.p11[1] = tw[2]; a.p12[0] = d_p12; a.p12[1] = tw[3];
+        a.p21[0] = d_p21; a.p21[1] = tw[4]; a.p22[0] = d_p22; a.p22[1] = tw[5];
+    }
     a.w = w; a.h = h; a.pitch = pitch; a.l_t = l_t; a.theta = theta; a.taut = taut; a.one = 1.0f;
     a.scaled_eps = -1.f;   // never stops
     a.level = 0; a.slot = 0; a.mode = 0; a.inner_max = 1 << 30;
@@ -1217,6 +1286,7 @@ static int k_iterate_impl(int fused, const float* d_I1wx, const float* d_I1wy, c
     a.partials = (double*)(tmp + part_off);
     a.errlog = (double*)(tmp + log_off);
     int rc = TVL1_OK;
+    if (fused && (rc = make_iter_maps(a))) { cudaFree(tmp); return rc; }
     stage_begin(st);
     if (fused == 2) {
         // the shipped schedule: ONE cooperative k_outer launch runs all n iterations (two-iteration
@@ -1228,15 +1298,16 @@ static int k_iterate_impl(int fused, const float* d_I1wx, const float* d_I1wy, c
     stage_end(st);
     // passes made = buffer flips: n single passes, n/2 fused ones, n/2 + n%2 inside k_outer
     const int flips = fused == 2 ? n / 2 + (n & 1) : (fused ? n / 2 : n);
-    if (!rc && (flips & 1)) {
-        float* dst[6] = {d_u1, d_u2, d_p11, d_p12, d_p21, d_p22};
+    if (!rc && (fused || (flips & 1))) {
+        const int t = flips & 1;
+        float* const src[6] = {a.u1[t], a.u2[t], a.p11[t], a.p12[t], a.p21[t], a.p22[t]};
         for (int k = 0; k < 6 && !rc; k++)
-            if (cudaMemcpyAsync(dst[k], tw[k], pb, cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+            if (cudaMemcpyAsync(user[k], src[k], pb, cudaMemcpyDeviceToDevice, st) != cudaSuccess)
                 rc = fail(TVL1_ERR_CUDA, "copy back failed");
     }
     if (!rc && errors && n > 0 &&
-        cudaMemcpyAsync(errors, tmp + log_off, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st) != cudaSuccess)
-        rc = fail(TVL1_ERR_CUDA, "error log copy failed");
+        (e = cudaMemcpyAsync(errors, tmp + log_off, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st)) != cudaSuccess)
+        rc = fail(TVL1_ERR_CUDA, "error log copy failed: %s", cudaGetErrorString(e));
     e = cudaStreamSynchronize(st);
     if (!rc && e != cudaSuccess) rc = fail(TVL1_ERR_CUDA, "iterate: %s", cudaGetErrorString(e));
     cudaFree(tmp);
