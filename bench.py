@@ -399,7 +399,7 @@ def run_ours(args):
     volume = None
     if args.volume_pairs > 0:
         VS = args.volume_size
-        hs = chained(4, VS, 200 + rank)
+        hs = chained(4, VS, 200)   # the same slices on every rank: weak scaling then measures the machine, not the content
         v_solver = N.Solver(N.default_params(lambda_=0.15, nscales=5, warps=5, inner_iterations=30,
                                              outer_iterations=10), device=local)
 

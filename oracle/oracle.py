@@ -57,6 +57,9 @@ def lib():
     L.orc_iterate.argtypes = [_f32p] * 10 + [C.c_int, C.c_int, C.c_float, C.c_float, C.c_float,
                                              C.c_int]
     L.orc_iterate.restype = C.c_double
+    L.orc_iterate_gamma.argtypes = [_f32p] * 13 + [C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float,
+                                                   C.c_int]
+    L.orc_iterate_gamma.restype = C.c_double
     L.orc_median5.argtypes = [_f32p, C.c_int, C.c_int, _f32p]
     L.orc_median25_selftest.restype = C.c_long
     L.orc_pyramid_sizes.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, _i32p, _i32p]
@@ -146,6 +149,13 @@ def iterate(I1wx, I1wy, grad, rho_c, u1, u2, p11, p12, p21, p22, l_t, theta, tau
     h, w = u1.shape
     return lib().orc_iterate(_f32(I1wx), _f32(I1wy), _f32(grad), _f32(rho_c), u1, u2, p11, p12,
                              p21, p22, w, h, l_t, theta, taut, mode)
+
+
+def iterate_gamma(I1wx, I1wy, grad, rho_c, u1, u2, u3, p11, p12, p21, p22, p31, p32, l_t, theta, taut, gamma, mode=0):
+    """One inner iteration with the third channel (gamma != 0) IN PLACE on u1..u3, p11..p32.  Returns error."""
+    h, w = u1.shape
+    return lib().orc_iterate_gamma(_f32(I1wx), _f32(I1wy), _f32(grad), _f32(rho_c), u1, u2, u3, p11, p12,
+                                   p21, p22, p31, p32, w, h, l_t, theta, taut, gamma, mode)
 
 
 def median5(src):

@@ -244,6 +244,7 @@ void orc_warp(const float* I0, const float* I1, const float* I1x, const float* I
 
 typedef struct {
     float *v1, *v2, *div1, *div2, *u1x, *u1y, *u2x, *u2y;
+    float *v3, *div3, *u3x, *u3y;   /* gamma != 0 only (allocated on first use) */
     double* rowsum;
     size_t cap_px;
     int cap_rows;
@@ -253,6 +254,7 @@ static void ws_free(iter_ws* s)
 {
     free(s->v1); free(s->v2); free(s->div1); free(s->div2);
     free(s->u1x); free(s->u1y); free(s->u2x); free(s->u2y); free(s->rowsum);
+    free(s->v3); free(s->div3); free(s->u3x); free(s->u3y);
     memset(s, 0, sizeof(*s));
 }
 
@@ -407,6 +409,140 @@ static void estimate_dual(const float* u1x, const float* u1y, const float* u2x, 
     }
 }
 
+/* ---- gamma != 0: the third channel u3 / p31, p32 (illumination term) of OpenCV 3.4.1's
+ * tvl1flow.cpp (EstimateVBody, EstimateUBody, EstimateDualVariablesBody with use_gamma).
+ * As recalled: rho gains + gamma*u3 (added last), d3 = +-l_t*gamma or fi*gamma,
+ * v3 = u3 + d3, u3' = v3 + theta*div(p31, p32), the error term gains (u3' - u3)^2 (added last),
+ * p31/p32 are updated like the other dual variables; grad and rho_c do not involve gamma. */
+static void estimate_v_g(const float* I1wx, const float* I1wy, const float* u1, const float* u2,
+                         const float* u3, const float* grad, const float* rho_c, float* v1,
+                         float* v2, float* v3, int w, int h, float l_t, float gamma)
+{
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < h; y++) {
+        const size_t o = (size_t)y * w;
+        for (int x = 0; x < w; x++) {
+            const size_t i = o + x;
+            const float rho = rho_c[i] + (I1wx[i] * u1[i] + I1wy[i] * u2[i]) + gamma * u3[i];
+            float d1 = 0.0f, d2 = 0.0f, d3 = 0.0f;
+            if (rho < -l_t * grad[i]) {
+                d1 = l_t * I1wx[i];
+                d2 = l_t * I1wy[i];
+                d3 = l_t * gamma;
+            } else if (rho > l_t * grad[i]) {
+                d1 = -l_t * I1wx[i];
+                d2 = -l_t * I1wy[i];
+                d3 = -l_t * gamma;
+            } else if (grad[i] > FLT_EPSILON) {
+                const float fi = -rho / grad[i];
+                d1 = fi * I1wx[i];
+                d2 = fi * I1wy[i];
+                d3 = fi * gamma;
+            }
+            v1[i] = u1[i] + d1;
+            v2[i] = u2[i] + d2;
+            v3[i] = u3[i] + d3;
+        }
+    }
+}
+
+static double estimate_u_g(const float* v1, const float* v2, const float* v3, const float* div1,
+                           const float* div2, const float* div3, float* u1, float* u2, float* u3,
+                           int w, int h, float theta, int mode, double* rowsum)
+{
+    if (mode == 1) {
+        float error = 0.0f;
+        for (int y = 0; y < h; y++) {
+            const size_t o = (size_t)y * w;
+            for (int x = 0; x < w; x++) {
+                const size_t i = o + x;
+                const float u1k = u1[i], u2k = u2[i], u3k = u3[i];
+                u1[i] = v1[i] + theta * div1[i];
+                u2[i] = v2[i] + theta * div2[i];
+                u3[i] = v3[i] + theta * div3[i];
+                error += (u1[i] - u1k) * (u1[i] - u1k) + (u2[i] - u2k) * (u2[i] - u2k) +
+                         (u3[i] - u3k) * (u3[i] - u3k);
+            }
+        }
+        return (double)error;
+    }
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < h; y++) {
+        const size_t o = (size_t)y * w;
+        double acc = 0.0;
+        for (int x = 0; x < w; x++) {
+            const size_t i = o + x;
+            const float u1k = u1[i], u2k = u2[i], u3k = u3[i];
+            u1[i] = v1[i] + theta * div1[i];
+            u2[i] = v2[i] + theta * div2[i];
+            u3[i] = v3[i] + theta * div3[i];
+            const float term = (u1[i] - u1k) * (u1[i] - u1k) + (u2[i] - u2k) * (u2[i] - u2k) +
+                               (u3[i] - u3k) * (u3[i] - u3k);
+            acc += (double)term;
+        }
+        rowsum[y] = acc;
+    }
+    double error = 0.0;
+    for (int y = 0; y < h; y++) error += rowsum[y];
+    return error;
+}
+
+/* one channel of estimateDualVariables (the gamma = 0 form above does two at once) */
+static void estimate_dual1(const float* ux, const float* uy, float* p1, float* p2, int w, int h,
+                           float taut)
+{
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < h; y++) {
+        const size_t o = (size_t)y * w;
+        for (int x = 0; x < w; x++) {
+            const size_t i = o + x;
+            const float g = hypot_f(ux[i], uy[i]);
+            const float ng = 1.0f + taut * g;
+            p1[i] = (p1[i] + taut * ux[i]) / ng;
+            p2[i] = (p2[i] + taut * uy[i]) / ng;
+        }
+    }
+}
+
+static double iterate_ws_g(iter_ws* s, const float* I1wx, const float* I1wy, const float* grad,
+                           const float* rho_c, float* u1, float* u2, float* u3, float* p11,
+                           float* p12, float* p21, float* p22, float* p31, float* p32, int w, int h,
+                           float l_t, float theta, float taut, float gamma, int mode)
+{
+    const size_t n = (size_t)w * h;
+    if (!s->v3) {
+        s->v3 = (float*)malloc(s->cap_px * 4); s->div3 = (float*)malloc(s->cap_px * 4);
+        s->u3x = (float*)malloc(s->cap_px * 4); s->u3y = (float*)malloc(s->cap_px * 4);
+    }
+    (void)n;
+    estimate_v_g(I1wx, I1wy, u1, u2, u3, grad, rho_c, s->v1, s->v2, s->v3, w, h, l_t, gamma);
+    divergence(p11, p12, s->div1, w, h);
+    divergence(p21, p22, s->div2, w, h);
+    divergence(p31, p32, s->div3, w, h);
+    const double err = estimate_u_g(s->v1, s->v2, s->v3, s->div1, s->div2, s->div3, u1, u2, u3, w, h,
+                                    theta, mode, s->rowsum);
+    forward_gradient(u1, s->u1x, s->u1y, w, h);
+    forward_gradient(u2, s->u2x, s->u2y, w, h);
+    forward_gradient(u3, s->u3x, s->u3y, w, h);
+    estimate_dual(s->u1x, s->u1y, s->u2x, s->u2y, p11, p12, p21, p22, w, h, taut);
+    estimate_dual1(s->u3x, s->u3y, p31, p32, w, h, taut);
+    return err;
+}
+
+double orc_iterate_gamma(const float* I1wx, const float* I1wy, const float* grad, const float* rho_c,
+                         float* u1, float* u2, float* u3, float* p11, float* p12, float* p21,
+                         float* p22, float* p31, float* p32, int w, int h, float l_t, float theta,
+                         float taut, float gamma, int error_sum_mode)
+{
+    iter_ws s;
+    memset(&s, 0, sizeof(s));
+    if (ws_reserve(&s, w, h)) return -1.0;
+    const double e = iterate_ws_g(&s, I1wx, I1wy, grad, rho_c, u1, u2, u3, p11, p12, p21, p22, p31,
+                                  p32, w, h, l_t, theta, taut, gamma, error_sum_mode);
+    ws_free(&s);
+    return e;
+}
+
 static double iterate_ws(iter_ws* s, const float* I1wx, const float* I1wy, const float* grad,
                          const float* rho_c, float* u1, float* u2, float* p11, float* p12,
                          float* p21, float* p22, int w, int h, float l_t, float theta,
@@ -537,7 +673,6 @@ int orc_tvl1_calc(const orc_params* p, const unsigned char* I0, long pitch0,
                   float* u_out, float* v_out, int* iters_out)
 {
     if (!p || p->nscales <= 0 || p->nscales > ORC_MAX_LEVELS || w <= 0 || h <= 0) return -1;
-    if (p->gamma != 0.0) return -2;                       /* only gamma == 0 restated */
     if (p->median_filtering != 1 && p->median_filtering != 5) return -3;
 #ifdef _OPENMP
     if (p->nthreads > 0) omp_set_num_threads(p->nthreads);
@@ -581,6 +716,16 @@ int orc_tvl1_calc(const orc_params* p, const unsigned char* I0, long pitch0,
     float* p11 = (float*)malloc(n0 * 4); float* p12 = (float*)malloc(n0 * 4);
     float* p21 = (float*)malloc(n0 * 4); float* p22 = (float*)malloc(n0 * 4);
     float* med = (float*)malloc(n0 * 4);
+    /* gamma != 0: u3 per level (zero at the coarsest, resized -- not scaled -- between levels), p31, p32 */
+    const int use_gamma = p->gamma != 0.0;
+    const float gamma = (float)p->gamma;
+    float* u3s[ORC_MAX_LEVELS];
+    memset(u3s, 0, sizeof(u3s));
+    float *p31 = NULL, *p32 = NULL;
+    if (use_gamma) {
+        for (int s = 0; s < nscales; s++) u3s[s] = (float*)calloc((size_t)ws[s] * hs[s], 4);
+        p31 = (float*)malloc(n0 * 4); p32 = (float*)malloc(n0 * 4);
+    }
     iter_ws wsb;
     memset(&wsb, 0, sizeof(wsb));
     ws_reserve(&wsb, w, h);
@@ -598,6 +743,7 @@ int orc_tvl1_calc(const orc_params* p, const unsigned char* I0, long pitch0,
         orc_centered_gradient(I1s[s], lw, lh, I1x, I1y);
         memset(p11, 0, n * 4); memset(p12, 0, n * 4);
         memset(p21, 0, n * 4); memset(p22, 0, n * 4);
+        if (use_gamma) { memset(p31, 0, n * 4); memset(p32, 0, n * 4); }
         for (int warpings = 0; warpings < p->warps; ++warpings) {
             orc_warp(I0s[s], I1s[s], I1x, I1y, u1, u2, lw, lh, NULL, I1wx, I1wy, grad, rho_c);
             float error = FLT_MAX;
@@ -610,9 +756,12 @@ int orc_tvl1_calc(const orc_params* p, const unsigned char* I0, long pitch0,
                 }
                 for (int n_inner = 0; error > scaledEpsilon && n_inner < p->inner_iterations;
                      ++n_inner) {
-                    const double e = iterate_ws(&wsb, I1wx, I1wy, grad, rho_c, u1, u2, p11, p12,
-                                                p21, p22, lw, lh, l_t, theta, taut,
-                                                p->error_sum_mode);
+                    const double e = use_gamma
+                        ? iterate_ws_g(&wsb, I1wx, I1wy, grad, rho_c, u1, u2, u3s[s], p11, p12, p21, p22,
+                                       p31, p32, lw, lh, l_t, theta, taut, gamma, p->error_sum_mode)
+                        : iterate_ws(&wsb, I1wx, I1wy, grad, rho_c, u1, u2, p11, p12,
+                                     p21, p22, lw, lh, l_t, theta, taut,
+                                     p->error_sum_mode);
                     /* the reference holds the error in a float; the canonical fp64 sum is
                      * rounded to fp32 once here so that the comparison is float > float */
                     error = (float)e;
@@ -626,6 +775,7 @@ int orc_tvl1_calc(const orc_params* p, const unsigned char* I0, long pitch0,
         const float up = (float)(1 / p->scale_step);
         orc_resize_linear(u1, lw, lh, u1s[s - 1], ws[s - 1], hs[s - 1], 0.0);
         orc_resize_linear(u2, lw, lh, u2s[s - 1], ws[s - 1], hs[s - 1], 0.0);
+        if (use_gamma) orc_resize_linear(u3s[s], lw, lh, u3s[s - 1], ws[s - 1], hs[s - 1], 0.0);
         const size_t nn = (size_t)ws[s - 1] * hs[s - 1];
         float *a = u1s[s - 1], *b = u2s[s - 1];
 #pragma omp parallel for schedule(static)
@@ -637,6 +787,8 @@ int orc_tvl1_calc(const orc_params* p, const unsigned char* I0, long pitch0,
     for (int s = 0; s < ORC_MAX_LEVELS; s++) { free(I0s[s]); free(I1s[s]); free(u1s[s]); free(u2s[s]); }
     free(I1x); free(I1y); free(I1wx); free(I1wy); free(grad); free(rho_c);
     free(p11); free(p12); free(p21); free(p22); free(med);
+    for (int s = 0; s < ORC_MAX_LEVELS; s++) free(u3s[s]);
+    free(p31); free(p32);
     ws_free(&wsb);
     return nscales;
 }

@@ -32,7 +32,7 @@ typedef struct orc_params {
     double theta;            /* 0.3 */
     double epsilon;          /* 0.01 */
     double scale_step;       /* 0.8 */
-    double gamma;            /* 0 (only gamma == 0 is restated) */
+    double gamma;            /* 0; != 0: the third channel u3 / p31, p32 (as recalled) */
     int nscales;             /* OpenCV 5; reference wrapper 10 (src/optflow.cpp:506) */
     int warps;               /* 5 */
     int inner_iterations;    /* 30 */
@@ -72,6 +72,12 @@ void orc_warp(const float* I0, const float* I1, const float* I1x, const float* I
 double orc_iterate(const float* I1wx, const float* I1wy, const float* grad, const float* rho_c,
                    float* u1, float* u2, float* p11, float* p12, float* p21, float* p22,
                    int w, int h, float l_t, float theta, float taut, int error_sum_mode);
+
+/* A.5 with gamma != 0: the same iteration with the third channel (u3, p31, p32). */
+double orc_iterate_gamma(const float* I1wx, const float* I1wy, const float* grad, const float* rho_c,
+                         float* u1, float* u2, float* u3, float* p11, float* p12, float* p21,
+                         float* p22, float* p31, float* p32, int w, int h, float l_t, float theta,
+                         float taut, float gamma, int error_sum_mode);
 
 /* A.7: exact 5x5 median, replicate border; dst may equal src. */
 void orc_median5(const float* src, int w, int h, float* dst);
