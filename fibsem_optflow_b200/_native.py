@@ -83,7 +83,7 @@ EXPORTS = [
     "tvl1_prescaled_size", "tvl1_prescale_u8", "tvl1_prescale_u8_host",
     "tvl1_mask_flow_u8", "tvl1_finish_flow_u8", "tvl1_sample_matches", "tvl1_sample_matches_skip", "tvl1_sample_matches_ex",
     "tvl1_default_feature_params", "tvl1_find_alignment", "tvl1_warp_affine_u8", "tvl1_warp_affine_f32", "tvl1_stack_run", "tvl1_k_convert_u8", "tvl1_k_resize",
-    "tvl1_k_centered_gradient", "tvl1_k_warp", "tvl1_k_iterate", "tvl1_k_iterate_fused2", "tvl1_k_outer", "tvl1_k_median5", "tvl1_k_last_ms",
+    "tvl1_k_centered_gradient", "tvl1_k_warp", "tvl1_k_iterate", "tvl1_k_iterate_fused2", "tvl1_k_outer", "tvl1_k_iterate_gamma", "tvl1_k_median5", "tvl1_k_last_ms",
     "tvl1_pyramid_sizes", "tvl1_glibc_rand", "tvl1_selftest_arith", "tvl1_dev_count", "tvl1_dev_alloc", "tvl1_dev_free",
     "tvl1_dev_memset", "tvl1_dev_h2d", "tvl1_dev_d2h", "tvl1_dev_sync", "tvl1_set_device", "tvl1_stream_create",
     "tvl1_stream_destroy", "tvl1_stream_sync", "tvl1_stream_query", "tvl1_stream_wait", "tvl1_dev_h2d_async", "tvl1_dev_d2h_async",
@@ -152,6 +152,8 @@ def lib():
                                               C.c_float, C.c_int, _vp, _vp]
     L.tvl1_k_iterate_fused2.argtypes = L.tvl1_k_iterate.argtypes
     L.tvl1_k_outer.argtypes = L.tvl1_k_iterate.argtypes
+    L.tvl1_k_iterate_gamma.argtypes = [_vp] * 12 + [C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float,
+                                                    C.c_float, C.c_int, _vp, _vp]
     L.tvl1_prescaled_size.argtypes = [C.c_int, C.c_int, C.c_double, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.tvl1_prescale_u8.argtypes = [_vp, _sz, C.c_int, C.c_int, C.c_double, _vp, _sz, _vp]
     L.tvl1_prescale_u8_host.argtypes = [C.c_int, _vp, _sz, C.c_int, C.c_int, C.c_double, _vp, _sz]
@@ -547,6 +549,17 @@ def k_iterate(I1wx, I1wy, grad, rho_c, u1, u2, p11, p12, p21, p22, l_t, theta, t
     fn = lib().tvl1_k_outer if fused == "outer" else (lib().tvl1_k_iterate_fused2 if fused else lib().tvl1_k_iterate)
     check(fn(*[p.ptr for p in consts], *[p.ptr for p in state], w, h,
              state[0].pitch, l_t, theta, taut, n, errs.ctypes.data, None))
+    return tuple(p.get() for p in state) + (errs[:n],)
+
+
+def k_iterate_gamma(I1wx, I1wy, rho_c, u1, u2, u3, p11, p12, p21, p22, p31, p32, l_t, theta, taut, gamma, n=1, device=0):
+    """n iterations of the three-channel form (gamma != 0); returns (u1,u2,u3,p11..p32, errors[n])."""
+    h, w = np.asarray(u1).shape
+    consts = [Plane(h, w, device, np.asarray(a, np.float32)) for a in (I1wx, I1wy, rho_c)]
+    state = [Plane(h, w, device, np.asarray(a, np.float32)) for a in (u1, u2, u3, p11, p12, p21, p22, p31, p32)]
+    errs = np.zeros(max(n, 1), np.float64)
+    check(lib().tvl1_k_iterate_gamma(*[p.ptr for p in consts], *[p.ptr for p in state], w, h, state[0].pitch,
+                                     l_t, theta, taut, gamma, n, errs.ctypes.data, None))
     return tuple(p.get() for p in state) + (errs[:n],)
 
 

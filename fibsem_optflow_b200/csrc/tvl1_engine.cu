@@ -401,6 +401,28 @@ int launch_iterate2(IterArgs& a, cudaStream_t st)
     return TVL1_OK;
 }
 
+// gamma != 0: one inner iteration = estimateU launch + dual-update launch (persistent blocks over row segments)
+int launch_gamma_iteration(const GammaArgs& a, cudaStream_t st)
+{
+    static int cached[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int& resident = cached[dev & 63];
+    if (!resident) {
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        resident = sms * 8;
+    }
+    const long long ntiles = (long long)cdiv(a.w, 128) * a.h;
+    const long long want = (ntiles + ITER_NW - 1) / ITER_NW;
+    const unsigned grid = (unsigned)(want < resident ? want : resident);
+    dim3 b(32, ITER_NW);
+    k_gamma_u<ITER_NW><<<grid, b, 0, st>>>(a);
+    k_gamma_p<ITER_NW><<<grid, b, 0, st>>>(a);
+    CK(cudaGetLastError());
+    return TVL1_OK;
+}
+
 int launch_median(const MedianArgs& a, int planes, cudaStream_t st)
 {
     // persistent blocks: one grid of resident blocks walks the tile list of both planes
@@ -455,6 +477,10 @@ struct tvl1_handle {
     float *I1wx = nullptr, *I1wy = nullptr, *rho = nullptr;   // warp outputs (I1x, I1y, grad never exist as planes)
     float *u1x = nullptr, *u2x = nullptr;   // twin [1] of u, shared by all levels
     float* p[4][2] = {{nullptr}};           // p11,p12,p21,p22 twins
+    // gamma != 0 only: u3 per level, p31, p32 (their own allocation, made on first use)
+    char* garena = nullptr;
+    float* u3[TVL1_MAX_LEVELS] = {};
+    float *p31 = nullptr, *p32 = nullptr;
     Ctrl* d_ctrl = nullptr;
     Ctrl* h_ctrl = nullptr;                 // pinned
     double* d_partials = nullptr;
@@ -500,6 +526,8 @@ static int get_event(tvl1_handle* H, cudaEvent_t* out)
 
 static void release_arena(tvl1_handle* H)
 {
+    if (H->garena) cudaFree(H->garena);
+    H->garena = nullptr;
     if (H->arena) cudaFree(H->arena);
     H->arena = nullptr;
     H->arena_bytes = 0;
@@ -580,6 +608,28 @@ static int ensure_capacity(tvl1_handle* H, int w, int h, cudaStream_t st)
     return TVL1_OK;
 }
 
+// planes of the third channel (gamma != 0): sized like the arena they accompany, released with it
+static int ensure_gamma(tvl1_handle* H, cudaStream_t st)
+{
+    if (H->prm.gamma == 0.0 || H->garena) return TVL1_OK;
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+    size_t o3[TVL1_MAX_LEVELS];
+    for (int s = 0; s < H->nlevels; s++) o3[s] = carve((size_t)H->lv[s].pitch * H->lv[s].h * sizeof(float));
+    const size_t b0 = (size_t)H->lv[0].pitch * H->lv[0].h * sizeof(float);
+    const size_t o31 = carve(b0), o32 = carve(b0);
+    cudaError_t e = cudaMalloc(&H->garena, off);
+    if (e != cudaSuccess) {
+        H->garena = nullptr;
+        return fail(TVL1_ERR_NOMEM, "cudaMalloc(%zu bytes) for the gamma planes failed: %s", off, cudaGetErrorString(e));
+    }
+    for (int s = 0; s < H->nlevels; s++) H->u3[s] = (float*)(H->garena + o3[s]);
+    H->p31 = (float*)(H->garena + o31);
+    H->p32 = (float*)(H->garena + o32);
+    CK(cudaMemsetAsync(H->garena, 0, off, st));
+    return TVL1_OK;
+}
+
 static int resolve_iterations(tvl1_handle* H)
 {
     const tvl1_params& p = H->prm;
@@ -603,7 +653,7 @@ static int check_params(const tvl1_params* p)
     if (p->warps <= 0 || p->warps > TVL1_MAX_WARPS) return fail(TVL1_ERR_INVALID, "warps out of range");
     if (!(p->scale_step > 0.0 && p->scale_step < 1.0)) return fail(TVL1_ERR_INVALID, "scaleStep must be in (0,1)");
     if (p->scale_step == 0.5) return fail(TVL1_ERR_UNSUPPORTED, "scaleStep == 0.5 takes OpenCV's INTER_AREA path, not restated");
-    if (p->gamma != 0.0) return fail(TVL1_ERR_UNSUPPORTED, "gamma != 0 is not supported");
+    if (!(p->gamma == p->gamma)) return fail(TVL1_ERR_INVALID, "gamma is not a number");
     if (p->use_initial_flow) return fail(TVL1_ERR_UNSUPPORTED, "useInitialFlow is not supported (the reference never forwards it)");
     if (p->median_filtering != 1 && p->median_filtering != 5)
         return fail(TVL1_ERR_UNSUPPORTED, "medianFiltering must be 1 or 5");
@@ -625,6 +675,7 @@ static int calc_device(tvl1_handle* H, const uint8_t* f0, size_t pitch0, const u
     CK(cudaSetDevice(H->device));
     int rc;
     if ((rc = ensure_capacity(H, w, h, st))) return rc;
+    if ((rc = ensure_gamma(H, st))) return rc;
     if ((rc = upload_cubic_table(H->device))) return rc;
     const tvl1_params& P = H->prm;
     const int L = H->nlevels, W = P.warps;
@@ -668,6 +719,7 @@ static int calc_device(tvl1_handle* H, const uint8_t* f0, size_t pitch0, const u
         const size_t b = (size_t)c.pitch * c.h * sizeof(float);
         CK(cudaMemsetAsync(c.u1, 0, b, st));
         CK(cudaMemsetAsync(c.u2, 0, b, st));
+        if (P.gamma != 0.0) CK(cudaMemsetAsync(H->u3[L - 1], 0, b, st));
     }
     CK(cudaEventRecord(ev_pyr, st));
 
@@ -682,6 +734,7 @@ static int calc_device(tvl1_handle* H, const uint8_t* f0, size_t pitch0, const u
         const float scaled_eps = (float)(P.epsilon * P.epsilon * (double)(lv.w * lv.h));
         if ((rc = span_begin(3, s))) return rc;
         for (int k = 0; k < 4; k++) CK(cudaMemsetAsync(H->p[k][0], 0, pb, st));
+        if (P.gamma != 0.0) { CK(cudaMemsetAsync(H->p31, 0, pb, st)); CK(cudaMemsetAsync(H->p32, 0, pb, st)); }
         span_end();
 
         IterArgs ia;
@@ -693,6 +746,20 @@ static int calc_device(tvl1_handle* H, const uint8_t* f0, size_t pitch0, const u
         ia.level = s; ia.ctrl = H->d_ctrl; ia.partials = H->d_partials; ia.errlog = nullptr;
         ia.mode = 0; ia.inner_max = H->inner;
         ia.tm = lv.tm_iter;
+        const bool with_gamma = P.gamma != 0.0;
+        GammaArgs ga;
+        if (with_gamma) {
+            ga.I1wx = H->I1wx; ga.I1wy = H->I1wy; ga.rho_c = H->rho;
+            for (int k = 0; k < 2; k++) {
+                ga.u1[k] = ia.u1[k]; ga.u2[k] = ia.u2[k];
+                ga.p11[k] = ia.p11[k]; ga.p12[k] = ia.p12[k]; ga.p21[k] = ia.p21[k]; ga.p22[k] = ia.p22[k];
+            }
+            ga.u3 = H->u3[s]; ga.p31 = H->p31; ga.p32 = H->p32;
+            ga.w = lv.w; ga.h = lv.h; ga.pitch = lv.pitch;
+            ga.l_t = l_t; ga.theta = theta; ga.taut = taut; ga.gamma = (float)P.gamma; ga.scaled_eps = scaled_eps;
+            ga.level = s; ga.slot = 0; ga.inner_max = H->inner; ga.mode = 1;
+            ga.ctrl = H->d_ctrl; ga.partials = H->d_partials; ga.errlog = nullptr;
+        }
         const bool fused = (long long)lv.w * lv.h >= H->fused_min_px && H->inner >= 2;
         const bool multi = !fused && H->multi_iter && H->inner >= 2;
         MedianArgs ma;
@@ -739,7 +806,14 @@ static int calc_device(tvl1_handle* H, const uint8_t* f0, size_t pitch0, const u
                     const int left_pred = pred_total - done_total - done_inner;
                     want = want == 0 ? (left_pred + 1 > 4 ? left_pred + 1 : 4) : 2 * want;
                     if (want > H->inner - done_inner) want = H->inner - done_inner;
-                    if (fused && H->coop_outer) {
+                    if (with_gamma) {
+                        // the three-channel iteration: two plain launches each, no-ops once the stop flag is set
+                        ga.slot = slot;
+                        ga.errlog = ia.errlog;
+                        for (int k = 0; k < want; ++k)
+                            if ((rc = launch_gamma_iteration(ga, st))) return rc;
+                        launches += 2 * want;
+                    } else if (fused && H->coop_outer) {
                         // the whole inner loop of this outer iteration in one cooperative launch
                         IterArgs io = ia;
                         io.mode = 2;
@@ -798,6 +872,10 @@ static int calc_device(tvl1_handle* H, const uint8_t* f0, size_t pitch0, const u
         if ((rc = launch_resize2(uc ? H->u1x : lv.u1, uc ? H->u2x : lv.u2, lv.w, lv.h, lv.pitch, up.u1, up.u2, up.w, up.h,
                                  up.pitch, 0.0, mul, 1, st))) return rc;
         launches += 1;
+        if (with_gamma) {   // u3 is zoomed like the flow but not scaled
+            if ((rc = launch_resize(H->u3[s], lv.w, lv.h, lv.pitch, H->u3[s - 1], up.w, up.h, up.pitch, 0.0, 1.f, 0, st))) return rc;
+            launches += 1;
+        }
         span_end();
     }
     // A.8: planar output
@@ -1338,6 +1416,47 @@ int tvl1_k_outer(const float* d_I1wx, const float* d_I1wy, const float* d_grad, 
 {
     return k_iterate_impl(2, d_I1wx, d_I1wy, d_grad, d_rho_c, d_u1, d_u2, d_p11, d_p12, d_p21, d_p22, w, h, pitch,
                           l_t, theta, taut, n, errors, stream);
+}
+
+int tvl1_k_iterate_gamma(const float* d_I1wx, const float* d_I1wy, const float* d_rho_c,
+                         float* d_u1, float* d_u2, float* d_u3, float* d_p11, float* d_p12,
+                         float* d_p21, float* d_p22, float* d_p31, float* d_p32, int w, int h,
+                         int pitch, float l_t, float theta, float taut, float gamma, int n,
+                         double* errors, void* stream)
+{
+    if (!d_I1wx || !d_I1wy || !d_rho_c || !d_u1 || !d_u2 || !d_u3 || !d_p11 || !d_p12 || !d_p21 || !d_p22 ||
+        !d_p31 || !d_p32 || w <= 0 || h <= 0 || pitch % 4 || pitch < w || n < 0)
+        return fail(TVL1_ERR_INVALID, "bad argument");
+    if (n > TVL1_MAX_LEVELS * TVL1_MAX_WARPS) return fail(TVL1_ERR_INVALID, "n too large");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t nb = iterate_max_blocks();
+    char* tmp = nullptr;
+    const size_t part_off = 1024 * ((sizeof(Ctrl) + 1023) / 1024);
+    const size_t log_off = part_off + nb * sizeof(double);
+    const size_t total = log_off + (size_t)(n + 1) * sizeof(double);
+    CK(cudaMalloc(&tmp, total));
+    cudaError_t e = cudaMemsetAsync(tmp, 0, total, st);
+    if (e != cudaSuccess) { cudaFree(tmp); return fail(TVL1_ERR_CUDA, "memset: %s", cudaGetErrorString(e)); }
+    GammaArgs a;
+    a.I1wx = d_I1wx; a.I1wy = d_I1wy; a.rho_c = d_rho_c;
+    for (int k = 0; k < 2; k++) {
+        a.u1[k] = d_u1; a.u2[k] = d_u2; a.p11[k] = d_p11; a.p12[k] = d_p12; a.p21[k] = d_p21; a.p22[k] = d_p22;
+    }
+    a.u3 = d_u3; a.p31 = d_p31; a.p32 = d_p32;
+    a.w = w; a.h = h; a.pitch = pitch; a.l_t = l_t; a.theta = theta; a.taut = taut; a.gamma = gamma;
+    a.scaled_eps = -1.f; a.level = 0; a.slot = 0; a.inner_max = 1 << 30; a.mode = 0;
+    a.ctrl = (Ctrl*)tmp; a.partials = (double*)(tmp + part_off); a.errlog = (double*)(tmp + log_off);
+    int rc = TVL1_OK;
+    stage_begin(st);
+    for (int i = 0; i < n && !rc; i++) rc = launch_gamma_iteration(a, st);
+    stage_end(st);
+    if (!rc && errors && n > 0 &&
+        (e = cudaMemcpyAsync(errors, tmp + log_off, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st)) != cudaSuccess)
+        rc = fail(TVL1_ERR_CUDA, "error log copy failed: %s", cudaGetErrorString(e));
+    e = cudaStreamSynchronize(st);
+    if (!rc && e != cudaSuccess) rc = fail(TVL1_ERR_CUDA, "iterate (gamma): %s", cudaGetErrorString(e));
+    cudaFree(tmp);
+    return rc;
 }
 
 int tvl1_k_median5(const float* d_src, int w, int h, int pitch, float* d_dst, void* stream)

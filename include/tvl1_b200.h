@@ -66,7 +66,7 @@ typedef struct tvl1_params {
     double theta;           /* 0.3 */
     double epsilon;         /* 0.01 */
     double scale_step;      /* "scaleStep", 0.8 */
-    double gamma;           /* 0; only 0 is supported */
+    double gamma;           /* 0; != 0 adds OpenCV's third channel (u3, p31, p32): supported, on a plain two-launch iteration */
     int nscales;            /* reference wrapper default 10 (OpenCV 5) */
     int warps;              /* 5 */
     int iterations;         /* 300; used when inner/outer are <= 0:
@@ -283,6 +283,12 @@ int tvl1_k_iterate(const float* d_I1wx, const float* d_I1wy, const float* d_grad
                    const float* d_rho_c, float* d_u1, float* d_u2, float* d_p11, float* d_p12,
                    float* d_p21, float* d_p22, int w, int h, int pitch,
                    float l_t, float theta, float taut, int n, double* errors, void* stream);
+/* n inner iterations of the three-channel form (gamma != 0: u3, p31, p32 join), in place, no stop test */
+int tvl1_k_iterate_gamma(const float* d_I1wx, const float* d_I1wy, const float* d_rho_c,
+                         float* d_u1, float* d_u2, float* d_u3, float* d_p11, float* d_p12,
+                         float* d_p21, float* d_p22, float* d_p31, float* d_p32, int w, int h,
+                         int pitch, float l_t, float theta, float taut, float gamma, int n,
+                         double* errors, void* stream);
 /* same through the temporally blocked kernel (two iterations per launch); n must be even */
 int tvl1_k_iterate_fused2(const float* d_I1wx, const float* d_I1wy, const float* d_grad,
                           const float* d_rho_c, float* d_u1, float* d_u2, float* d_p11, float* d_p12,

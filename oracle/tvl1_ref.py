@@ -115,8 +115,41 @@ def iterate(I1wx, I1wy, grad, rho_c, u1, u2, p11, p12, p21, p22, l_t, theta, tau
     return nu1, nu2, p11, p12, p21, p22, error
 
 
+def iterate_gamma(I1wx, I1wy, grad, rho_c, u1, u2, u3, p11, p12, p21, p22, p31, p32, l_t, theta, taut, gamma):
+    """One inner iteration with the third channel (A.5, gamma != 0).
+    Returns new (u1,u2,u3,p11,p12,p21,p22,p31,p32,error)."""
+    l_t, theta, taut, gamma = F32(l_t), F32(theta), F32(taut), F32(gamma)
+    rho = (rho_c + (I1wx * u1 + I1wy * u2)) + gamma * u3
+    lg = l_t * grad
+    c1 = rho < -lg
+    c2 = (~c1) & (rho > lg)
+    c3 = (~c1) & (~c2) & (grad > FLT_EPSILON)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        fi = (-rho / grad).astype(F32)
+    zero = np.zeros_like(u1)
+    with np.errstate(invalid="ignore", over="ignore"):
+        d = []
+        for t in (I1wx, I1wy, np.full_like(u1, gamma)):
+            x = np.where(c1, l_t * t, zero)
+            x = np.where(c2, -l_t * t, x)
+            x = np.where(c3, fi * t, x).astype(F32)
+            d.append(x)
+    v = [u1 + d[0], u2 + d[1], u3 + d[2]]
+    div = [divergence(p11, p12), divergence(p21, p22), divergence(p31, p32)]
+    nu = [v[k] + theta * div[k] for k in range(3)]
+    e = [nu[0] - u1, nu[1] - u2, nu[2] - u3]
+    term = (e[0] * e[0] + e[1] * e[1]) + e[2] * e[2]
+    error = float(np.sum(term.astype(np.float64)))
+    out_p = []
+    for k, (pa, pb) in enumerate(((p11, p12), (p21, p22), (p31, p32))):
+        ux, uy = forward_gradient(nu[k])
+        ng = F32(1.0) + taut * hypot_f(ux, uy)
+        out_p += [(pa + taut * ux) / ng, (pb + taut * uy) / ng]
+    return (nu[0], nu[1], nu[2], *out_p, error)
+
+
 def tvl1_calc(I0u8, I1u8, tau=0.25, lambda_=0.15, theta=0.3, nscales=5, warps=5, epsilon=0.01,
-              inner_iterations=30, outer_iterations=10, scale_step=0.8, median_filtering=5):
+              inner_iterations=30, outer_iterations=10, scale_step=0.8, median_filtering=5, gamma=0.0):
     """Returns (u, v, iters[levels][warps])."""
     _need_cv2()
     I0s = [I0u8.astype(F32)]
@@ -136,6 +169,7 @@ def tvl1_calc(I0u8, I1u8, tau=0.25, lambda_=0.15, theta=0.3, nscales=5, warps=5,
     th = F32(theta)
     u1 = np.zeros_like(I0s[-1])
     u2 = np.zeros_like(I0s[-1])
+    u3 = np.zeros_like(I0s[-1])          # gamma != 0 only
     iters = np.full((nscales, warps), -1, np.int32)
     for s in range(nscales - 1, -1, -1):
         I0, I1 = I0s[s], I1s[s]
@@ -144,6 +178,7 @@ def tvl1_calc(I0u8, I1u8, tau=0.25, lambda_=0.15, theta=0.3, nscales=5, warps=5,
         I1x, I1y = centered_gradient(I1)
         p11 = np.zeros_like(I0); p12 = np.zeros_like(I0)
         p21 = np.zeros_like(I0); p22 = np.zeros_like(I0)
+        p31 = np.zeros_like(I0); p32 = np.zeros_like(I0)
         for wi in range(warps):
             _, I1wx, I1wy, grad, rho_c = warp(I0, I1, I1x, I1y, u1, u2)
             error = FLT_MAX
@@ -155,8 +190,12 @@ def tvl1_calc(I0u8, I1u8, tau=0.25, lambda_=0.15, theta=0.3, nscales=5, warps=5,
                     u2 = cv2.medianBlur(u2, median_filtering)
                 ni = 0
                 while error > scaled_eps and ni < inner_iterations:
-                    u1, u2, p11, p12, p21, p22, e = iterate(I1wx, I1wy, grad, rho_c, u1, u2,
-                                                            p11, p12, p21, p22, l_t, th, taut)
+                    if gamma != 0.0:
+                        u1, u2, u3, p11, p12, p21, p22, p31, p32, e = iterate_gamma(
+                            I1wx, I1wy, grad, rho_c, u1, u2, u3, p11, p12, p21, p22, p31, p32, l_t, th, taut, gamma)
+                    else:
+                        u1, u2, p11, p12, p21, p22, e = iterate(I1wx, I1wy, grad, rho_c, u1, u2,
+                                                                p11, p12, p21, p22, l_t, th, taut)
                     error = F32(e)
                     count += 1
                     ni += 1
@@ -168,4 +207,6 @@ def tvl1_calc(I0u8, I1u8, tau=0.25, lambda_=0.15, theta=0.3, nscales=5, warps=5,
         up = F32(1 / scale_step)
         u1 = cv2.resize(u1, (pw, ph), interpolation=cv2.INTER_LINEAR) * up
         u2 = cv2.resize(u2, (pw, ph), interpolation=cv2.INTER_LINEAR) * up
+        if gamma != 0.0:
+            u3 = cv2.resize(u3, (pw, ph), interpolation=cv2.INTER_LINEAR)   # zoomed, not scaled
     return u1, u2, iters

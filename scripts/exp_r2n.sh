@@ -1,0 +1,1 @@
+python -m pytest tests/test_gpu_solve.py tests/test_gpu_cli.py tests/test_gpu_stack.py -m gpu -x -q 2>&1 | tail -5

@@ -109,6 +109,25 @@ def test_iterate_fused2(gpu, orc, h, w, n):
     np.testing.assert_allclose(got[6], werr, rtol=1e-12)
 
 
+@pytest.mark.parametrize("h,w", SIZES + [(200, 700)])
+@pytest.mark.parametrize("n", [1, 4])
+def test_iterate_gamma(gpu, orc, h, w, n):
+    """the three-channel iteration (gamma != 0): same states and per-iteration errors as the oracle"""
+    rng = np.random.default_rng(15)
+    consts, state = make_iter_inputs(rng, h, w)
+    I1wx, I1wy, grad, rho_c = consts
+    u3, p31, p32 = rnd(rng, h, w, 0.6), rnd(rng, h, w, 0.4), rnd(rng, h, w, 0.4)
+    st = [state[0], state[1], u3] + state[2:] + [p31, p32]
+    l_t, theta, taut, gamma = np.float32(0.15 * 0.3), np.float32(0.3), np.float32(0.25 / 0.3), np.float32(0.35)
+    want = [s.copy() for s in st]
+    werr = [orc.iterate_gamma(I1wx, I1wy, grad, rho_c, *want, l_t, theta, taut, gamma) for _ in range(n)]
+    got = gpu.k_iterate_gamma(I1wx, I1wy, rho_c, *st, l_t, theta, taut, gamma, n=n)
+    names = ["u1", "u2", "u3", "p11", "p12", "p21", "p22", "p31", "p32"]
+    for k in range(9):
+        assert np.array_equal(got[k], want[k]), names[k]
+    np.testing.assert_allclose(got[9], werr, rtol=1e-12)
+
+
 @pytest.mark.parametrize("h,w", SIZES[:2] + [(200, 700)])
 @pytest.mark.parametrize("n", [1, 5, 8])
 def test_iterate_outer(gpu, orc, h, w, n):

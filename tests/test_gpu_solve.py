@@ -63,13 +63,44 @@ def test_handle_reuse_and_resize(gpu, orc):
         assert np.array_equal(u, ou) and np.array_equal(v, ov)
 
 
+@pytest.mark.parametrize("h,w,seed,kw", [
+    (192, 256, 7, dict(lambda_=0.15, nscales=5, gamma=0.25)),
+    (150, 131, 3, dict(lambda_=0.15, nscales=3, gamma=1.5, inner_iterations=9, outer_iterations=4)),
+    (96, 130, 5, dict(gamma=0.05, warps=2)),                                          # wrapper defaults otherwise
+    (128, 100, 2, dict(lambda_=0.15, nscales=4, gamma=0.4, median_filtering=1)),
+])
+def test_gamma_solve_is_exact(gpu, orc, h, w, seed, kw):
+    """gamma != 0 (the reference forwards the key, src/optflow.cpp:511,518): the third channel u3 / p31, p32;
+    flow bit-equal to the oracle, same iteration counts; a brightness offset between the frames so that the
+    illumination term has something to do; the handle goes back to gamma == 0 afterwards"""
+    I0, I1 = synth.make_pair(h, w, seed=seed)
+    I1 = np.clip(I1.astype(np.int32) + 7, 0, 255).astype(np.uint8)
+    s = gpu.Solver(gpu.default_params(**kw))
+    u, v = s.calc(I0, I1)
+    okw = {("lambda" if k == "lambda_" else k): val for k, val in kw.items()}
+    if "lambda" not in okw:
+        okw.update({"lambda": 0.05, "nscales": 10})
+    ou, ov, oit, lev = orc.tvl1_calc(I0, I1, **okw)
+    assert s.stats.levels == lev and np.array_equal(s.stats.iters_array(), oit[:lev])
+    assert np.array_equal(u, ou) and np.array_equal(v, ov)
+    kw0 = dict(kw, gamma=0.0)
+    s.set_params(gpu.default_params(**kw0))
+    u0, v0 = s.calc(I0, I1)
+    okw["gamma"] = 0.0
+    ou0, ov0, _, _ = orc.tvl1_calc(I0, I1, **okw)
+    assert np.array_equal(u0, ou0) and np.array_equal(v0, ov0)
+    s.close()
+
+
 def test_errors(gpu):
     import ctypes as C
     p = gpu.default_params()
     p.nscales = 0
     h = C.c_void_p()
     assert gpu.lib().tvl1_create(C.byref(p), 0, C.byref(h)) == -1
-    p = gpu.default_params(gamma=0.5)
+    p = gpu.default_params(gamma=float("nan"))
+    assert gpu.lib().tvl1_create(C.byref(p), 0, C.byref(h)) == -1
+    p = gpu.default_params(use_initial_flow=1)
     assert gpu.lib().tvl1_create(C.byref(p), 0, C.byref(h)) == -3
     s = gpu.Solver(gpu.default_params())
     with pytest.raises(gpu.Tvl1Error):

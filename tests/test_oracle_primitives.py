@@ -187,6 +187,44 @@ def test_iterate_vs_numpy(orc):
     assert abs(err - want[6]) <= 1e-12 * abs(err)
 
 
+def test_iterate_gamma_vs_numpy(orc):
+    """gamma != 0 (third channel u3 / p31, p32): the C oracle against the independently written NumPy form"""
+    from oracle import tvl1_ref
+    rng = np.random.default_rng(18)
+    h, w = 37, 70
+    f = lambda s: (rng.standard_normal((h, w)) * s).astype(np.float32)
+    I1wx, I1wy, rho_c = f(8), f(8), f(20)
+    z = rng.random((h, w)) < 0.05
+    I1wx[z] = 0
+    I1wy[z] = 0
+    grad = I1wx * I1wx + I1wy * I1wy
+    st = [f(0.8), f(0.8), f(0.5)] + [f(0.4) for _ in range(6)]
+    l_t, theta, taut, gamma = np.float32(0.045), np.float32(0.3), np.float32(0.25 / 0.3), np.float32(0.4)
+    want = [s.copy() for s in st]
+    got = [s.copy() for s in st]
+    for _ in range(3):
+        r = tvl1_ref.iterate_gamma(I1wx, I1wy, grad, rho_c, *want, l_t, theta, taut, gamma)
+        want, werr = list(r[:9]), r[9]
+        err = orc.iterate_gamma(I1wx, I1wy, grad, rho_c, *got, l_t, theta, taut, gamma)
+        for k in range(9):
+            assert np.array_equal(got[k], want[k]), k
+        assert abs(err - werr) <= 1e-12 * abs(err)
+
+
+def test_whole_pair_gamma_vs_cv2_composition(orc, cv2_plain):
+    """whole solve with gamma != 0: C oracle == cv2 composition; and gamma == 0 is untouched by the new path"""
+    from fibsem_optflow_b200 import synth
+    from oracle import tvl1_ref
+    I0, I1 = synth.make_pair(96, 128, seed=21, dx=1.1, dy=-0.4)
+    I1 = np.clip(I1.astype(np.int32) + 9, 0, 255).astype(np.uint8)     # a brightness change: what gamma is for
+    u, v, it, lev = orc.tvl1_calc(I0, I1, gamma=0.25, nscales=4)
+    ru, rv, rit = tvl1_ref.tvl1_calc(I0, I1, gamma=0.25, nscales=4)
+    assert lev == rit.shape[0] and np.array_equal(it[:lev], rit)
+    assert np.array_equal(u, ru) and np.array_equal(v, rv)
+    u0, v0, _, _ = orc.tvl1_calc(I0, I1, nscales=4)
+    assert not np.array_equal(u, u0)
+
+
 def test_prescale_golden(orc):
     """8-bit cv::resize of the reference's loader (src/optflow.cpp:111,124) against cv2-made vectors:
     0.5 (area path, odd sizes included) and general factors (11-bit fixed-point bilinear)."""
