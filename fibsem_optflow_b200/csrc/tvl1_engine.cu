@@ -733,7 +733,7 @@ static int calc_device(tvl1_handle* H, const uint8_t* f0, size_t pitch0, const u
         const size_t pb = (size_t)lv.pitch * lv.h * sizeof(float);
         const float scaled_eps = (float)(P.epsilon * P.epsilon * (double)(lv.w * lv.h));
         if ((rc = span_begin(3, s))) return rc;
-        for (int k = 0; k < 4; k++) CK(cudaMemsetAsync(H->p[k][0], 0, pb, st));
+        // p11 .. p22 start a level at zero: the level's first warp kernel writes the zeros (WarpArgs::pz)
         if (P.gamma != 0.0) { CK(cudaMemsetAsync(H->p31, 0, pb, st)); CK(cudaMemsetAsync(H->p32, 0, pb, st)); }
         span_end();
 
@@ -780,6 +780,7 @@ static int calc_device(tvl1_handle* H, const uint8_t* f0, size_t pitch0, const u
             ma.slot = slot;
             // (2) warp I1 by the current flow; also re-arms the stop test (error = FLT_MAX)
             if ((rc = span_begin(1, s))) return rc;
+            for (int k = 0; k < 4; k++) wa.pz[k] = wi == 0 ? H->p[k][0] : nullptr;
             if ((rc = launch_warp(wa, st))) return rc;
             launches++;
             span_end();
@@ -1308,6 +1309,7 @@ int tvl1_k_warp(const float* d_I0, const float* d_I1, const float* d_u1, const f
     a.u1[0] = a.u1[1] = d_u1; a.u2[0] = a.u2[1] = d_u2;
     a.I1w = d_I1w; a.I1wx = d_I1wx; a.I1wy = d_I1wy; a.grad = d_grad; a.rho_c = d_rho_c;
     a.w = w; a.h = h; a.pitch = pitch; a.level = -1; a.ctrl = nullptr;
+    for (int k = 0; k < 4; k++) a.pz[k] = nullptr;
     for (int k = 0; k < 2; k++)
         if ((rc = make_plane_map(&a.tmI1[k], d_I1, pitch, h, TVL1_WP_RW, k == 0 ? 16 : TVL1_WP_RH))) return rc;
     stage_begin((cudaStream_t)stream);
