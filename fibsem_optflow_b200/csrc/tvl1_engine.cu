@@ -770,7 +770,7 @@ static int calc_device(tvl1_handle* H, const uint8_t* f0, size_t pitch0, const u
         wa.I0 = lv.I0; wa.I1 = lv.I1;
         wa.u1[0] = lv.u1; wa.u1[1] = H->u1x; wa.u2[0] = lv.u2; wa.u2[1] = H->u2x;
         wa.I1w = nullptr; wa.I1wx = H->I1wx; wa.I1wy = H->I1wy; wa.grad = nullptr; wa.rho_c = H->rho;
-        wa.w = lv.w; wa.h = lv.h; wa.pitch = lv.pitch; wa.level = s; wa.ctrl = H->d_ctrl;
+        wa.w = lv.w; wa.h = lv.h; wa.pitch = lv.pitch; wa.level = s; wa.ctrl = H->d_ctrl; wa.one = 1.0f;
         memcpy(wa.tmI1, lv.tm_I1, sizeof(wa.tmI1));
 
         for (int wi = 0; wi < W; ++wi) {
@@ -1308,7 +1308,7 @@ int tvl1_k_warp(const float* d_I0, const float* d_I1, const float* d_u1, const f
     a.I0 = d_I0; a.I1 = d_I1;
     a.u1[0] = a.u1[1] = d_u1; a.u2[0] = a.u2[1] = d_u2;
     a.I1w = d_I1w; a.I1wx = d_I1wx; a.I1wy = d_I1wy; a.grad = d_grad; a.rho_c = d_rho_c;
-    a.w = w; a.h = h; a.pitch = pitch; a.level = -1; a.ctrl = nullptr;
+    a.w = w; a.h = h; a.pitch = pitch; a.level = -1; a.ctrl = nullptr; a.one = 1.0f;
     for (int k = 0; k < 4; k++) a.pz[k] = nullptr;
     for (int k = 0; k < 2; k++)
         if ((rc = make_plane_map(&a.tmI1[k], d_I1, pitch, h, TVL1_WP_RW, k == 0 ? 16 : TVL1_WP_RH))) return rc;
