@@ -31,6 +31,32 @@ def draw(rng):
     return h, w, kw, pair, bands
 
 
+@pytest.mark.parametrize("h,w", [(1, 1), (1, 9), (2, 3), (4, 4), (3, 130), (130, 3), (5, 300), (16, 17), (15, 40), (33, 1)])
+@pytest.mark.parametrize("gamma", [0.0, 0.3])
+def test_degenerate_sizes(gpu, orc, h, w, gamma):
+    """frames smaller than a tile, a strip, a median window or the pyramid's 16-px stop rule (one level only):
+    every schedule bit-exact against the oracle"""
+    rng = np.random.default_rng(h * 1000 + w)
+    I0 = rng.integers(0, 256, (h, w), dtype=np.uint8)
+    I1 = np.roll(I0, 1, axis=1) if w > 1 else I0.copy()
+    I1 = (I1.astype(np.int32) * 7 // 8 + 3).astype(np.uint8)
+    kw = dict(lambda_=0.15, nscales=5, warps=3, inner_iterations=5, outer_iterations=3, gamma=gamma)
+    okw = {("lambda" if k == "lambda_" else k): v for k, v in kw.items()}
+    ou, ov, oit, olev = orc.tvl1_calc(I0, I1, **okw)
+    for fused_min, multi, coop in ((0, 1, 1), (0, 1, 0), (1e18, 1, 1), (1e18, 0, 1)):
+        s = gpu.Solver(gpu.default_params(**kw))
+        s.set_option("fused_min_px", fused_min)
+        s.set_option("multi_iter", multi)
+        s.set_option("coop_outer", coop)
+        u, v = s.calc(I0, I1)
+        assert s.stats.levels == olev
+        assert np.array_equal(s.stats.iters_array(), oit[:olev]), (h, w, fused_min, multi, coop)
+        assert np.array_equal(u, ou) and np.array_equal(v, ov), (h, w, fused_min, multi, coop)
+        s.close()
+        if gamma != 0.0:
+            break          # the three-channel iteration has one schedule
+
+
 @pytest.mark.parametrize("case", range(24))
 def test_random_config(gpu, orc, case):
     rng = np.random.default_rng(1000 + case)
