@@ -83,7 +83,7 @@ EXPORTS = [
     "tvl1_prescaled_size", "tvl1_prescale_u8", "tvl1_prescale_u8_host",
     "tvl1_mask_flow_u8", "tvl1_finish_flow_u8", "tvl1_sample_matches", "tvl1_sample_matches_skip", "tvl1_sample_matches_ex",
     "tvl1_default_feature_params", "tvl1_find_alignment", "tvl1_warp_affine_u8", "tvl1_warp_affine_f32", "tvl1_stack_run", "tvl1_k_convert_u8", "tvl1_k_resize",
-    "tvl1_k_centered_gradient", "tvl1_k_warp", "tvl1_k_iterate", "tvl1_k_iterate_fused2", "tvl1_k_outer", "tvl1_k_iterate_gamma", "tvl1_k_median5", "tvl1_k_last_ms",
+    "tvl1_k_centered_gradient", "tvl1_k_warp", "tvl1_k_iterate", "tvl1_k_iterate_fused2", "tvl1_k_outer", "tvl1_k_iterate_gamma", "tvl1_k_median5", "tvl1_k_median3", "tvl1_k_last_ms",
     "tvl1_pyramid_sizes", "tvl1_glibc_rand", "tvl1_selftest_arith", "tvl1_dev_count", "tvl1_dev_alloc", "tvl1_dev_free",
     "tvl1_dev_memset", "tvl1_dev_h2d", "tvl1_dev_d2h", "tvl1_dev_sync", "tvl1_set_device", "tvl1_stream_create",
     "tvl1_stream_destroy", "tvl1_stream_sync", "tvl1_stream_query", "tvl1_stream_wait", "tvl1_dev_h2d_async", "tvl1_dev_d2h_async",
@@ -158,6 +158,7 @@ def lib():
     L.tvl1_prescale_u8.argtypes = [_vp, _sz, C.c_int, C.c_int, C.c_double, _vp, _sz, _vp]
     L.tvl1_prescale_u8_host.argtypes = [C.c_int, _vp, _sz, C.c_int, C.c_int, C.c_double, _vp, _sz]
     L.tvl1_k_median5.argtypes = [_vp, C.c_int, C.c_int, C.c_int, _vp, _vp]
+    L.tvl1_k_median3.argtypes = L.tvl1_k_median5.argtypes
     L.tvl1_k_last_ms.argtypes = [C.POINTER(C.c_float)]
     L.tvl1_pyramid_sizes.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, _vp, _vp]
     L.tvl1_glibc_rand.argtypes = [C.c_longlong, C.c_longlong, C.c_int, _vp]
@@ -584,6 +585,16 @@ def warp_affine(src, affine, dsize, device=0):
     bs.free()
     bd.free()
     return out
+
+
+def k_median3(src, device=0):
+    src = np.asarray(src, np.float32)
+    h, w = src.shape
+    s = Plane(h, w, device, src)
+    d = Plane(h, w, device)
+    check(lib().tvl1_k_median3(s.ptr, w, h, s.pitch, d.ptr, None))
+    check(lib().tvl1_dev_sync(device))
+    return d.get()
 
 
 def k_median5(src, device=0):

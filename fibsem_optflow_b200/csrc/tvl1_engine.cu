@@ -190,6 +190,12 @@ int launch_resize2(const float* srcA, const float* srcB, int sw, int sh, int sp,
     else { inv_x = (double)dw / sw; inv_y = (double)dh / sh; }
     const double scale_x = 1. / inv_x, scale_y = 1. / inv_y;
     dim3 b(32, 8);
+    if (inv_scale == 0.5 && !apply_mul) {   // resize(src, Size(), 0.5, 0.5): OpenCV's INTER_AREA fast path
+        dim3 gh(cdiv(dw, 32), cdiv(dh, 8), srcB ? 2 : 1);
+        k_resize_half<<<gh, b, 0, st>>>(srcA, srcB, sw, sh, sp, dstA, dstB, dw, dh, dp);
+        CK(cudaGetLastError());
+        return TVL1_OK;
+    }
     dim3 g(cdiv(cdiv(dw, 4), 32), cdiv(dh, 8), srcB ? 2 : 1);
     k_resize<<<g, b, 0, st>>>(srcA, srcB, sw, sh, sp, dstA, dstB, dw, dh, dp, scale_x, scale_y, mul, apply_mul);
     CK(cudaGetLastError());
@@ -423,6 +429,18 @@ int launch_gamma_iteration(const GammaArgs& a, cudaStream_t st)
     return TVL1_OK;
 }
 
+int launch_median3(const MedianArgs& a, int planes, cudaStream_t st)
+{
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long n = (long long)cdiv(a.w, 4) * a.h * planes;
+    const long long want = (n + 255) / 256;
+    k_median3<<<(unsigned)(want < sms * 8 ? want : sms * 8), 256, 0, st>>>(a, planes);
+    CK(cudaGetLastError());
+    return TVL1_OK;
+}
+
 int launch_median(const MedianArgs& a, int planes, cudaStream_t st)
 {
     // persistent blocks: one grid of resident blocks walks the tile list of both planes
@@ -652,11 +670,10 @@ static int check_params(const tvl1_params* p)
     if (p->nscales > TVL1_MAX_LEVELS) return fail(TVL1_ERR_INVALID, "nscales > %d", TVL1_MAX_LEVELS);
     if (p->warps <= 0 || p->warps > TVL1_MAX_WARPS) return fail(TVL1_ERR_INVALID, "warps out of range");
     if (!(p->scale_step > 0.0 && p->scale_step < 1.0)) return fail(TVL1_ERR_INVALID, "scaleStep must be in (0,1)");
-    if (p->scale_step == 0.5) return fail(TVL1_ERR_UNSUPPORTED, "scaleStep == 0.5 takes OpenCV's INTER_AREA path, not restated");
     if (!(p->gamma == p->gamma)) return fail(TVL1_ERR_INVALID, "gamma is not a number");
     if (p->use_initial_flow) return fail(TVL1_ERR_UNSUPPORTED, "useInitialFlow is not supported (the reference never forwards it)");
-    if (p->median_filtering != 1 && p->median_filtering != 5)
-        return fail(TVL1_ERR_UNSUPPORTED, "medianFiltering must be 1 or 5");
+    if (p->median_filtering != 1 && p->median_filtering != 3 && p->median_filtering != 5)   // cv::medianBlur's fp32 apertures
+        return fail(TVL1_ERR_UNSUPPORTED, "medianFiltering must be 1 (off), 3 or 5");
     if (!(p->theta > 0.0)) return fail(TVL1_ERR_INVALID, "theta must be > 0");
     if (!(p->lambda >= 0.0)) return fail(TVL1_ERR_INVALID, "lambda must be >= 0");   // the threshold step assumes l_t * grad >= 0
     return TVL1_OK;
@@ -795,7 +812,7 @@ static int calc_device(tvl1_handle* H, const uint8_t* f0, size_t pitch0, const u
             for (int no = 0; no < H->outer; ++no) {
                 if (P.median_filtering > 1) {
                     if ((rc = span_begin(2, s))) return rc;
-                    if ((rc = launch_median(ma, 2, st))) return rc;
+                    if ((rc = P.median_filtering == 3 ? launch_median3(ma, 2, st) : launch_median(ma, 2, st))) return rc;
                     launches++;
                     span_end();
                 }
@@ -1472,6 +1489,20 @@ int tvl1_k_median5(const float* d_src, int w, int h, int pitch, float* d_dst, vo
     if (int r = make_plane_map(&a.tm[0][0], d_src, pitch, h, TVL1_MED_SW, TVL1_MED_SH)) return r;
     stage_begin((cudaStream_t)stream);
     const int rc = launch_median(a, 1, (cudaStream_t)stream);
+    stage_end((cudaStream_t)stream);
+    return rc;
+}
+
+int tvl1_k_median3(const float* d_src, int w, int h, int pitch, float* d_dst, void* stream)
+{
+    if (!d_src || !d_dst || d_src == d_dst || w <= 0 || h <= 0 || pitch % 4 || pitch < w)
+        return fail(TVL1_ERR_INVALID, "bad argument");
+    MedianArgs a;
+    a.u1[0] = const_cast<float*>(d_src); a.u1[1] = d_dst; a.u2[0] = a.u2[1] = nullptr;
+    a.w = w; a.h = h; a.pitch = pitch; a.level = -1; a.slot = 0; a.ctrl = nullptr;
+    memset(a.tm, 0, sizeof(a.tm));
+    stage_begin((cudaStream_t)stream);
+    const int rc = launch_median3(a, 1, (cudaStream_t)stream);
     stage_end((cudaStream_t)stream);
     return rc;
 }

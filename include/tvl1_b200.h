@@ -73,7 +73,7 @@ typedef struct tvl1_params {
                                inner = 30, outer = ceil(iterations / 30) */
     int inner_iterations;   /* <= 0: derive from iterations */
     int outer_iterations;   /* <= 0: derive from iterations */
-    int median_filtering;   /* 5 (CPU class); 1 = off */
+    int median_filtering;   /* 5 (CPU class); 3; 1 = off */
     int use_initial_flow;   /* read by the reference but never forwarded
                                (src/optflow.cpp:512,518); must be 0 */
     int reserved[3];
@@ -301,6 +301,8 @@ int tvl1_k_outer(const float* d_I1wx, const float* d_I1wy, const float* d_grad,
                  float* d_p21, float* d_p22, int w, int h, int pitch,
                  float l_t, float theta, float taut, int n, double* errors, void* stream);
 int tvl1_k_median5(const float* d_src, int w, int h, int pitch, float* d_dst, void* stream);
+/* medianBlur(src, 3): the other fp32 aperture (medianFiltering = 3) */
+int tvl1_k_median3(const float* d_src, int w, int h, int pitch, float* d_dst, void* stream);
 /* CUDA-event time of the kernel launches of the calling thread's most recent tvl1_k_warp /
  * tvl1_k_iterate / tvl1_k_median5 call (waits for them). */
 int tvl1_k_last_ms(float* ms);

@@ -62,6 +62,7 @@ def lib():
     L.orc_iterate_gamma.restype = C.c_double
     L.orc_median5.argtypes = [_f32p, C.c_int, C.c_int, _f32p]
     L.orc_median25_selftest.restype = C.c_long
+    L.orc_median3.argtypes = [_f32p, C.c_int, C.c_int, _f32p]
     L.orc_pyramid_sizes.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, _i32p, _i32p]
     L.orc_pyramid_sizes.restype = C.c_int
     L.orc_tvl1_calc.argtypes = [C.POINTER(OrcParams), _u8p, C.c_long, _u8p, C.c_long, C.c_int,
@@ -163,6 +164,14 @@ def median5(src):
     h, w = src.shape
     dst = np.empty_like(src)
     lib().orc_median5(src, w, h, dst)
+    return dst
+
+
+def median3(src):
+    src = _f32(src)
+    h, w = src.shape
+    dst = np.empty_like(src)
+    lib().orc_median3(src, w, h, dst)
     return dst
 
 

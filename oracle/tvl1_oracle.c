@@ -53,6 +53,37 @@ int orc_scaled_size(int n, double f)
 void orc_resize_linear(const float* src, int sw, int sh, float* dst, int dw, int dh,
                        double inv_scale)
 {
+    if (inv_scale == 0.5) {
+        /* resize(src, Size(), 0.5, 0.5, INTER_LINEAR) is switched to INTER_AREA by cv::resize (scale exactly
+         * 2: the "area fast" path).  The mean of a 2x2 block is ((a + b) + (c + d)) * 0.25f in the SIMD part of
+         * a row (four destination pixels at a time, ResizeAreaFastVec_SIMD_32f) and (((a + b) + c) + d) * 0.25f
+         * for the up to three whole blocks left over; a block that hangs over the source (destination size
+         * rounded up) is the mean of the pixels that exist, summed in row-major order and divided by their
+         * count.  Pinned against cv2 on 300 random sizes (tests/test_oracle_primitives.py). */
+        const int vec = (sw / 2) / 4 * 4;   /* destination columns the 4-wide loop covers */
+#pragma omp parallel for schedule(static)
+        for (int dy = 0; dy < dh; dy++)
+            for (int dx = 0; dx < dw; dx++) {
+                const int sx = 2 * dx, sy = 2 * dy;
+                float d;
+                if (sx + 1 < sw && sy + 1 < sh) {
+                    const float* S0 = src + (size_t)sy * sw + sx;
+                    const float* S1 = S0 + sw;
+                    d = dx < vec ? ((S0[0] + S0[1]) + (S1[0] + S1[1])) * 0.25f
+                                 : (S0[0] + S0[1] + S1[0] + S1[1]) * 0.25f;
+                } else if (sx >= sw || sy >= sh) {
+                    d = 0.f;
+                } else {
+                    float sum = 0.f;
+                    int count = 0;
+                    for (int r = 0; r < 2 && sy + r < sh; r++)
+                        for (int c = 0; c < 2 && sx + c < sw; c++) { sum += src[(size_t)(sy + r) * sw + sx + c]; count++; }
+                    d = sum / (float)count;
+                }
+                dst[(size_t)dy * dw + dx] = d;
+            }
+        return;
+    }
     double inv_x, inv_y;
     if (inv_scale > 0) { inv_x = inv_scale; inv_y = inv_scale; }
     else { inv_x = (double)dw / sw; inv_y = (double)dh / sh; }
@@ -653,6 +684,39 @@ void orc_median5(const float* src_in, int w, int h, float* dst)
     free(copy);
 }
 
+/* medianBlur(src, 3) on fp32: exact median of the 3x3 window, replicate border (the only other
+ * aperture cv::medianBlur accepts for CV_32F).  Selection by a plain insertion sort. */
+void orc_median3(const float* src_in, int w, int h, float* dst)
+{
+    const float* src = src_in;
+    float* copy = NULL;
+    if (src_in == dst) {
+        copy = (float*)malloc(sizeof(float) * (size_t)w * h);
+        memcpy(copy, src_in, sizeof(float) * (size_t)w * h);
+        src = copy;
+    }
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            float v[9];
+            int n = 0;
+            for (int k = -1; k <= 1; k++)
+                for (int j = -1; j <= 1; j++) {
+                    int yy = y + k, xx = x + j;
+                    if (yy < 0) yy = 0;
+                    if (yy > h - 1) yy = h - 1;
+                    if (xx < 0) xx = 0;
+                    if (xx > w - 1) xx = w - 1;
+                    const float t = src[(size_t)yy * w + xx];
+                    int i = n++;
+                    while (i > 0 && v[i - 1] > t) { v[i] = v[i - 1]; i--; }
+                    v[i] = t;
+                }
+            dst[(size_t)y * w + x] = v[4];
+        }
+    free(copy);
+}
+
 /* ---------------------------------------------------------- A.2/A.6/A.8 solve */
 
 int orc_pyramid_sizes(int w, int h, int nscales, double scale_step, int* ws, int* hs)
@@ -673,7 +737,7 @@ int orc_tvl1_calc(const orc_params* p, const unsigned char* I0, long pitch0,
                   float* u_out, float* v_out, int* iters_out)
 {
     if (!p || p->nscales <= 0 || p->nscales > ORC_MAX_LEVELS || w <= 0 || h <= 0) return -1;
-    if (p->median_filtering != 1 && p->median_filtering != 5) return -3;
+    if (p->median_filtering != 1 && p->median_filtering != 3 && p->median_filtering != 5) return -3;
 #ifdef _OPENMP
     if (p->nthreads > 0) omp_set_num_threads(p->nthreads);
 #endif
@@ -750,9 +814,12 @@ int orc_tvl1_calc(const orc_params* p, const unsigned char* I0, long pitch0,
             int count = 0;
             for (int n_outer = 0; error > scaledEpsilon && n_outer < p->outer_iterations;
                  ++n_outer) {
-                if (p->median_filtering > 1) {
+                if (p->median_filtering == 5) {
                     orc_median5(u1, lw, lh, med); memcpy(u1, med, n * 4);
                     orc_median5(u2, lw, lh, med); memcpy(u2, med, n * 4);
+                } else if (p->median_filtering == 3) {
+                    orc_median3(u1, lw, lh, med); memcpy(u1, med, n * 4);
+                    orc_median3(u2, lw, lh, med); memcpy(u2, med, n * 4);
                 }
                 for (int n_inner = 0; error > scaledEpsilon && n_inner < p->inner_iterations;
                      ++n_inner) {

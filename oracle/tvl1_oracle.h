@@ -37,7 +37,7 @@ typedef struct orc_params {
     int warps;               /* 5 */
     int inner_iterations;    /* 30 */
     int outer_iterations;    /* 10 */
-    int median_filtering;    /* 5 (1 = off; only 1 and 5 are restated) */
+    int median_filtering;    /* 5 (1 = off; 3 and 5 are the apertures cv::medianBlur has for fp32) */
     int error_sum_mode;      /* 0 = fp32 terms summed in fp64 (canonical)
                                 1 = one serial fp32 scalar, row-major (OpenCV literal) */
     int nthreads;            /* OpenMP threads, 0 = default */
@@ -81,6 +81,9 @@ double orc_iterate_gamma(const float* I1wx, const float* I1wy, const float* grad
 
 /* A.7: exact 5x5 median, replicate border; dst may equal src. */
 void orc_median5(const float* src, int w, int h, float* dst);
+
+/* medianBlur(src, 3): exact 3x3 median, replicate border; dst may equal src. */
+void orc_median3(const float* src, int w, int h, float* dst);
 
 /* number of pyramid levels actually used (A.2 stop rule) and their sizes */
 int orc_pyramid_sizes(int w, int h, int nscales, double scale_step, int* ws, int* hs);

@@ -33,6 +33,17 @@ def test_resize_down_and_up(gpu, orc, h, w):
     assert np.array_equal(got_up, want_up)
 
 
+@pytest.mark.parametrize("h,w", SIZES + [(2, 5), (3, 7), (31, 17), (33, 130)])
+def test_resize_half(gpu, orc, h, w):
+    """scaleStep == 0.5: OpenCV's INTER_AREA fast path (2x2 means; pairwise / sequential sums, partial border blocks)"""
+    rng = np.random.default_rng(h * 1000 + w + 7)
+    src = (rng.random((h, w)) * 255).astype(np.float32)
+    want = orc.resize_scale(src, 0.5)
+    got = gpu.k_resize(src, inv_scale=0.5)
+    assert got.shape == want.shape
+    assert np.array_equal(got, want)
+
+
 @pytest.mark.parametrize("h,w", SIZES)
 def test_centered_gradient(gpu, orc, h, w):
     rng = np.random.default_rng(1)
@@ -64,6 +75,16 @@ def test_median5(gpu, orc, h, w):
     rng = np.random.default_rng(3)
     src = rnd(rng, h, w, 3.0)
     assert np.array_equal(gpu.k_median5(src), orc.median5(src))
+
+
+@pytest.mark.parametrize("h,w", SIZES + [(1, 1), (1, 9), (7, 1), (3, 2)])
+def test_median3(gpu, orc, h, w):
+    """the 3x3 aperture (medianFiltering = 3), ties and zeros included"""
+    rng = np.random.default_rng(23)
+    src = rnd(rng, h, w, 3.0)
+    src[rng.random((h, w)) < 0.2] = 0
+    src[rng.random((h, w)) < 0.1] = 1.5
+    assert np.array_equal(gpu.k_median3(src), orc.median3(src))
 
 
 def make_iter_inputs(rng, h, w):

@@ -28,6 +28,13 @@ def draw(rng):
     pair = dict(seed=int(rng.integers(1, 10_000)), dx=float(rng.uniform(-3, 3)), dy=float(rng.uniform(-3, 3)),
                 shear=float(rng.uniform(-0.01, 0.01)), sigma=float(rng.choice([1.5, 2.0, 3.0])))
     bands = bool(rng.integers(0, 3) == 0)
+    # drawn last, so that the cases above keep their values: the INTER_AREA pyramid, the 3x3 median, gamma
+    if rng.random() < 0.2:
+        kw["scale_step"] = 0.5
+    if rng.random() < 0.2 and kw["median_filtering"] == 5:
+        kw["median_filtering"] = 3
+    if rng.random() < 0.15:
+        kw["gamma"] = float(rng.choice([0.1, 0.5]))
     return h, w, kw, pair, bands
 
 

@@ -92,6 +92,44 @@ def test_gamma_solve_is_exact(gpu, orc, h, w, seed, kw):
     s.close()
 
 
+@pytest.mark.parametrize("h,w,seed,kw", [
+    (180, 240, 6, dict(lambda_=0.15, nscales=4, median_filtering=3)),
+    (97, 133, 8, dict(median_filtering=3, warps=3)),
+    (128, 160, 4, dict(lambda_=0.15, nscales=3, median_filtering=3, gamma=0.2, inner_iterations=10, outer_iterations=5)),
+])
+def test_median3_solve_is_exact(gpu, orc, h, w, seed, kw):
+    """medianFiltering = 3 (cv::medianBlur's other fp32 aperture): flow bit-equal to the oracle, same iteration counts"""
+    I0, I1 = synth.make_pair(h, w, seed=seed)
+    s = gpu.Solver(gpu.default_params(**kw))
+    u, v = s.calc(I0, I1)
+    okw = {("lambda" if k == "lambda_" else k): val for k, val in kw.items()}
+    if "lambda" not in okw:
+        okw.update({"lambda": 0.05, "nscales": 10})
+    ou, ov, oit, lev = orc.tvl1_calc(I0, I1, **okw)
+    assert s.stats.levels == lev and np.array_equal(s.stats.iters_array(), oit[:lev])
+    assert np.array_equal(u, ou) and np.array_equal(v, ov)
+    s.close()
+
+
+@pytest.mark.parametrize("h,w,seed,kw", [
+    (200, 263, 6, dict(lambda_=0.15, nscales=4, scale_step=0.5)),
+    (131, 97, 8, dict(scale_step=0.5, warps=3)),                       # as many halvings as fit; odd sizes on the way
+    (256, 512, 4, dict(lambda_=0.15, nscales=5, scale_step=0.5, median_filtering=3)),
+])
+def test_scale_half_solve_is_exact(gpu, orc, h, w, seed, kw):
+    """scaleStep == 0.5: the pyramid takes OpenCV's INTER_AREA fast path (2x2 means); flow bit-equal to the oracle"""
+    I0, I1 = synth.make_pair(h, w, seed=seed)
+    s = gpu.Solver(gpu.default_params(**kw))
+    u, v = s.calc(I0, I1)
+    okw = {("lambda" if k == "lambda_" else k): val for k, val in kw.items()}
+    if "lambda" not in okw:
+        okw.update({"lambda": 0.05, "nscales": 10})
+    ou, ov, oit, lev = orc.tvl1_calc(I0, I1, **okw)
+    assert s.stats.levels == lev and np.array_equal(s.stats.iters_array(), oit[:lev])
+    assert np.array_equal(u, ou) and np.array_equal(v, ov)
+    s.close()
+
+
 def test_errors(gpu):
     import ctypes as C
     p = gpu.default_params()
@@ -101,6 +139,8 @@ def test_errors(gpu):
     p = gpu.default_params(gamma=float("nan"))
     assert gpu.lib().tvl1_create(C.byref(p), 0, C.byref(h)) == -1
     p = gpu.default_params(use_initial_flow=1)
+    assert gpu.lib().tvl1_create(C.byref(p), 0, C.byref(h)) == -3
+    p = gpu.default_params(median_filtering=7)
     assert gpu.lib().tvl1_create(C.byref(p), 0, C.byref(h)) == -3
     s = gpu.Solver(gpu.default_params())
     with pytest.raises(gpu.Tvl1Error):

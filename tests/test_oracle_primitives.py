@@ -187,6 +187,48 @@ def test_iterate_vs_numpy(orc):
     assert abs(err - want[6]) <= 1e-12 * abs(err)
 
 
+def test_resize_half_vs_cv2(orc, cv2_plain):
+    """scaleStep == 0.5: cv::resize(INTER_LINEAR) by exactly 1/2 is OpenCV's INTER_AREA fast path (4-wide pairwise
+    sums, sequential leftovers, partial blocks at a rounded-up border): bit-equal on random sizes"""
+    cv2 = cv2_plain
+    rng = np.random.default_rng(41)
+    for _ in range(120):
+        h, w = int(rng.integers(2, 70)), int(rng.integers(2, 90))
+        a = (rng.random((h, w)) * 255).astype(np.float32)
+        want = cv2.resize(a, None, fx=0.5, fy=0.5, interpolation=cv2.INTER_LINEAR)
+        assert np.array_equal(orc.resize_scale(a, 0.5), want), (h, w)
+
+
+def test_whole_pair_scale_half_vs_cv2_composition(orc, cv2_plain):
+    from fibsem_optflow_b200 import synth
+    from oracle import tvl1_ref
+    I0, I1 = synth.make_pair(150, 190, seed=5)
+    u, v, it, lev = orc.tvl1_calc(I0, I1, scale_step=0.5, nscales=4)
+    ru, rv, rit = tvl1_ref.tvl1_calc(I0, I1, scale_step=0.5, nscales=4)
+    assert lev == rit.shape[0] and np.array_equal(it[:lev], rit)
+    assert np.array_equal(u, ru) and np.array_equal(v, rv)
+
+
+def test_median3_vs_cv2(orc, cv2_plain):
+    """the 3x3 aperture (medianFiltering = 3) against cv2.medianBlur, degenerate sizes included"""
+    cv2 = cv2_plain
+    rng = np.random.default_rng(31)
+    for h, w in [(1, 1), (1, 7), (5, 1), (2, 2), (37, 53), (64, 131)]:
+        a = (rng.standard_normal((h, w)) * 3).astype(np.float32)
+        a[rng.random((h, w)) < 0.2] = 0
+        assert np.array_equal(orc.median3(a), cv2.medianBlur(a, 3)), (h, w)
+
+
+def test_whole_pair_median3_vs_cv2_composition(orc, cv2_plain):
+    from fibsem_optflow_b200 import synth
+    from oracle import tvl1_ref
+    I0, I1 = synth.make_pair(90, 120, seed=13)
+    u, v, it, lev = orc.tvl1_calc(I0, I1, median_filtering=3, nscales=4)
+    ru, rv, rit = tvl1_ref.tvl1_calc(I0, I1, median_filtering=3, nscales=4)
+    assert lev == rit.shape[0] and np.array_equal(it[:lev], rit)
+    assert np.array_equal(u, ru) and np.array_equal(v, rv)
+
+
 def test_iterate_gamma_vs_numpy(orc):
     """gamma != 0 (third channel u3 / p31, p32): the C oracle against the independently written NumPy form"""
     from oracle import tvl1_ref
