@@ -94,9 +94,35 @@ print(json.dumps(v))
     return out
 
 
+def primitives2():
+    """Round 2 additions (own generator and file, so that the round-1 fixtures stay byte-identical):
+    the 3x3 median, the scale-0.5 pyramid step (cv::resize's INTER_AREA fast path) on odd and even sizes,
+    and whole-pair flows of the cv2 composition with medianFiltering 3 / scaleStep 0.5."""
+    r2 = np.random.default_rng(20261019)
+    out = {}
+    med_in = (r2.standard_normal((37, 53)) * 3).astype(np.float32)
+    med_in[r2.random(med_in.shape) < 0.2] = 0
+    out["med3_in"] = med_in
+    out["med3"] = cv2.medianBlur(med_in, 3)
+    for k, (h, w) in enumerate([(37, 53), (31, 17), (40, 56), (7, 10), (3, 7)]):
+        a = (r2.random((h, w)) * 255).astype(np.float32)
+        out["half_in_%d" % k] = a
+        out["half_%d" % k] = cv2.resize(a, None, fx=0.5, fy=0.5, interpolation=cv2.INTER_LINEAR)
+    I0, I1 = synth.make_pair(90, 120, seed=13)
+    out["I0"], out["I1"] = I0, I1
+    out["u_med3"], out["v_med3"], out["it_med3"] = tvl1_ref.tvl1_calc(I0, I1, median_filtering=3, nscales=4)
+    out["u_half"], out["v_half"], out["it_half"] = tvl1_ref.tvl1_calc(I0, I1, scale_step=0.5, nscales=4)
+    np.savez_compressed(os.path.join(HERE, "primitives2.npz"), **out)
+
+
 def main():
+    if "--round2" in sys.argv:
+        primitives2()
+        print("primitives2.npz written to", HERE)
+        return
     sizes = primitives()
     pair()
+    primitives2()
     known = {
         "resize_sizes_0.8": sizes,
         "glibc_rand": glibc(),

@@ -39,3 +39,18 @@ def test_pair_golden(gpu):
     u, v = s2.calc(g["I0"], g["I1"])
     assert np.array_equal(s2.stats.iters_array(), g["iters_ref"])
     assert np.array_equal(u, g["u_ref"]) and np.array_equal(v, g["v_ref"])
+
+
+def test_round2_golden(gpu):
+    """3x3 median, scale-0.5 pyramid step and the whole-pair flows with medianFiltering 3 / scaleStep 0.5
+    against the cv2-made vectors of tests/golden/make_golden.py --round2"""
+    g = np.load(os.path.join(GOLD, "primitives2.npz"))
+    assert np.array_equal(gpu.k_median3(g["med3_in"]), g["med3"])
+    for k in range(5):
+        assert np.array_equal(gpu.k_resize(g["half_in_%d" % k], inv_scale=0.5), g["half_%d" % k]), k
+    for tag, kw in (("med3", dict(median_filtering=3)), ("half", dict(scale_step=0.5))):
+        s = gpu.Solver(gpu.default_params(lambda_=0.15, nscales=4, **kw))
+        u, v = s.calc(g["I0"], g["I1"])
+        assert np.array_equal(s.stats.iters_array(), g["it_" + tag]), tag
+        assert np.array_equal(u, g["u_" + tag]) and np.array_equal(v, g["v_" + tag]), tag
+        s.close()

@@ -209,6 +209,19 @@ def test_whole_pair_scale_half_vs_cv2_composition(orc, cv2_plain):
     assert np.array_equal(u, ru) and np.array_equal(v, rv)
 
 
+def test_round2_golden(orc):
+    """committed cv2-made vectors (tests/golden/make_golden.py --round2): 3x3 median, scale-0.5 pyramid step, and
+    whole-pair flows of the cv2 composition with medianFiltering 3 / scaleStep 0.5"""
+    g = np.load(os.path.join(GOLD, "primitives2.npz"))
+    assert np.array_equal(orc.median3(g["med3_in"]), g["med3"])
+    for k in range(5):
+        assert np.array_equal(orc.resize_scale(g["half_in_%d" % k], 0.5), g["half_%d" % k]), k
+    u, v, it, lev = orc.tvl1_calc(g["I0"], g["I1"], median_filtering=3, nscales=4)
+    assert np.array_equal(it[:lev], g["it_med3"]) and np.array_equal(u, g["u_med3"]) and np.array_equal(v, g["v_med3"])
+    u, v, it, lev = orc.tvl1_calc(g["I0"], g["I1"], scale_step=0.5, nscales=4)
+    assert np.array_equal(it[:lev], g["it_half"]) and np.array_equal(u, g["u_half"]) and np.array_equal(v, g["v_half"])
+
+
 def test_median3_vs_cv2(orc, cv2_plain):
     """the 3x3 aperture (medianFiltering = 3) against cv2.medianBlur, degenerate sizes included"""
     cv2 = cv2_plain
