@@ -102,7 +102,7 @@ struct FrameSlot {
 
 struct Driver {
     int device = 0;
-    int prefetch = 4;       // pairs whose frames are decoded ahead on host threads
+    int prefetch = 8;       // pairs whose frames are decoded ahead on host threads
     tvl1_handle* solver = nullptr;
     tvl1_params cur{};
     bool have_params = false;
@@ -117,6 +117,9 @@ struct Driver {
     long long rand_skip = 0;   // debug mode: one rand() stream for the whole process
     int uploads = 0;
     int shard = 0, nshards = 1, skipped = 0;
+    // --timing: where the wall time of a job goes (seconds): waiting for a frame's decode, staging, solving + outputs
+    bool timing = false;
+    double t_decode_wait = 0, t_stage = 0, t_solve = 0, t_lookahead = 0, t_points = 0, t_tail = 0, t_setup = 0;
     mj::Value all_matches = mj::Value::array();   // every batch so far, for the "matches_file" key
 
     ~Driver()
@@ -504,6 +507,7 @@ void solve_rois(Driver& D, const FrameSlot& f0, const FrameSlot& f1_in, const Va
 // from_file (src/optflow.cpp:75-178)
 int from_file(Driver& D, Value& args, int shard, int nshards)
 {
+    const auto tsu0 = std::chrono::steady_clock::now();
     const Value images = args.at("images");
     if (!images.isArray()) die("\"images\" must be an array");
     // The reference keeps the previous pair's decoded frames so that a slice shared by adjacent pairs (q
@@ -521,6 +525,16 @@ int from_file(Driver& D, Value& args, int shard, int nshards)
     long long last_upload = (long long)begin;   // the batch counter starts where this shard starts
     D.shard = shard; D.nshards = nshards;
     D.pool.device = D.device;
+    // the first pair's frames start decoding before this process has even touched CUDA: creating the context
+    // takes as long as decoding a slice, and the two overlap
+    if (D.prefetch > 0 && begin < end) {
+        const Value& first = images[begin];
+        if (first.isMember("p") && first.isMember("q") && first.at("p").type == Value::String && first.at("q").type == Value::String) {
+            prefetch(first.at("p").asString());
+            if (first.at("q").asString() != first.at("p").asString()) prefetch(first.at("q").asString());
+        }
+    }
+    if (tvl1_dev_count() <= 0) die("no CUDA device: this driver has no CPU path");
     if (tvl1_stream_create(D.device, &D.s_solve) < 0 || tvl1_stream_create(D.device, &D.s_copy) < 0)
         die(std::string("stream creation: ") + tvl1_last_error());
     auto scale_of = [&](const Value& im) { return im.get("scale", args.get("scale", Value(0.5))).asFloat(); };
@@ -536,6 +550,7 @@ int from_file(Driver& D, Value& args, int shard, int nshards)
             if (&sl != keep0 && &sl != keep1 && (!v || sl.last_use < v->last_use)) v = &sl;
         return v;
     };
+    D.t_setup = std::chrono::duration<double>(std::chrono::steady_clock::now() - tsu0).count();
     for (size_t i = begin; i < end; i++) {
         Value im = images[i];
         std::string n0, n1;
@@ -548,6 +563,13 @@ int from_file(Driver& D, Value& args, int shard, int nshards)
         // 8k x 8k PNG takes far longer than its solve, so the look-ahead -- not the GPU -- sets the pace
         // of a job); a frame that is on the device already, or that an earlier look-ahead covers, is not
         // decoded twice
+        const auto tl0 = std::chrono::steady_clock::now();
+        // this pair's own frames first, both at once, if nobody has them yet (the first pair of a job, or a pair
+        // that shares no slice with its predecessor): otherwise they would be decoded one after the other below
+        if (D.prefetch > 0) {
+            if (!find_slot(n0, scale)) prefetch(n0);
+            if (n1 != n0 && !find_slot(n1, scale)) prefetch(n1);
+        }
         {
             std::string prev0 = n0, prev1 = n1;
             for (size_t j = i + 1; j < end && j <= i + (size_t)D.prefetch; j++) {
@@ -562,19 +584,24 @@ int from_file(Driver& D, Value& args, int shard, int nshards)
             }
         }
         recycle_uploads(D, false);
+        D.t_lookahead += std::chrono::duration<double>(std::chrono::steady_clock::now() - tl0).count();
         // this pair's frames: on the device already, or decoded (by the look-ahead, else now) and staged
         auto fetch = [&](const std::string& name, const FrameSlot* keep) -> FrameSlot* {
             if (FrameSlot* sl = find_slot(name, scale)) { sl->last_use = (long long)i; return sl; }
             Decoded d;
+            const auto tw0 = std::chrono::steady_clock::now();
             auto it = inflight.find(name);
             if (it != inflight.end()) { d = it->second.get(); inflight.erase(it); }
             else d = decode_frame(name, pool);
+            const auto tw1 = std::chrono::steady_clock::now();
+            D.t_decode_wait += std::chrono::duration<double>(tw1 - tw0).count();
             if (!d.ok) {
                 std::cout << "Error: " << name << " (" << d.err << ")\n";   // :108-112, :120-124: log, next pair
                 return nullptr;
             }
             FrameSlot* sl = victim(keep, nullptr);
             stage_frame(D, *sl, name, scale, d);
+            D.t_stage += std::chrono::duration<double>(std::chrono::steady_clock::now() - tw1).count();
             sl->last_use = (long long)i;
             return sl;
         };
@@ -616,7 +643,11 @@ int from_file(Driver& D, Value& args, int shard, int nshards)
         std::snprintf(buffer, sizeof(buffer), "%0.2f", scale);
         if (!im.isMember("output"))
             im["output"] = Value(args.at("output_dir").asString() + "/" + im.at("output_name").asString() + "_" + buffer);
-        solve_rois(D, *f0, *f1, rois, im, args);
+        {
+            const auto ts0 = std::chrono::steady_clock::now();
+            solve_rois(D, *f0, *f1, rois, im, args);
+            D.t_solve += std::chrono::duration<double>(std::chrono::steady_clock::now() - ts0).count();
+        }
         } catch (const std::exception& e) {   // PairError, or a missing / mistyped key of this pair
             std::cout << "Error: pair " << n0 << " " << n1 << " skipped (" << e.what() << ")\n";
             std::cerr << "optflow_b200: pair " << i << " skipped: " << e.what() << "\n";
@@ -624,6 +655,7 @@ int from_file(Driver& D, Value& args, int shard, int nshards)
             continue;
         }
 
+        const auto tp0 = std::chrono::steady_clock::now();
         if (pick(im, args, "output_type", Value("map")).asString() == "random_points") {
             any_upload_since = true;
             if ((long long)i > last_upload + args.get("batch_size", Value(100)).asInt()) {
@@ -633,7 +665,9 @@ int from_file(Driver& D, Value& args, int shard, int nshards)
                 any_upload_since = false;
             }
         }
+        D.t_points += std::chrono::duration<double>(std::chrono::steady_clock::now() - tp0).count();
     }
+    const auto tt0 = std::chrono::steady_clock::now();
     if (any_upload_since) upload_points(D, args);
     bool ok = true;
     for (auto& w : D.writers) ok = w.get() && ok;
@@ -643,6 +677,7 @@ int from_file(Driver& D, Value& args, int shard, int nshards)
         if (d.px) D.pool.put(d.px, d.cap);
     }
     recycle_uploads(D, true);
+    D.t_tail = std::chrono::duration<double>(std::chrono::steady_clock::now() - tt0).count();
     return ok ? 0 : 2;
 }
 
@@ -651,14 +686,18 @@ int from_file(Driver& D, Value& args, int shard, int nshards)
 int main(int argc, const char* argv[])
 {
     std::string filename;
-    int device = 0, shard = 0, nshards = 1, prefetch = 4;
+    int device = 0, shard = 0, nshards = 1, prefetch = 8;
+    bool timing = false;
+    const auto t_start = std::chrono::steady_clock::now();
     for (int k = 1; k < argc; k++) {
         const std::string a = argv[k];
         if (a == "-h" || a == "--help") {
-            std::cout << "usage: optflow_b200 [--device N] [--shard RANK/WORLD] [--prefetch N] <job.json[.gz]>\n"
+            std::cout << "usage: optflow_b200 [--device N] [--shard RANK/WORLD] [--prefetch N] [--timing] <job.json[.gz]>\n"
                          "  --shard: solve only this rank's contiguous block of \"images\" (one process per GPU)\n"
-                         "  --prefetch: pairs whose frames are decoded ahead on host threads (default 4)\n";
+                         "  --prefetch: pairs whose frames are decoded ahead on host threads (default 8)\n";
             return 0;
+        } else if (a == "--timing") {
+            timing = true;
         } else if (a == "--device" && k + 1 < argc) {
             device = std::atoi(argv[++k]);
         } else if (a == "--prefetch" && k + 1 < argc) {
@@ -678,11 +717,21 @@ int main(int argc, const char* argv[])
     } catch (const std::exception& e) {
         die(std::string(e.what()) + " in " + filename);   // the reference ignores parse errors (:51,56); we do not
     }
-    if (tvl1_dev_count() <= 0) die("no CUDA device: this driver has no CPU path");
     const int style = (int)args.get("style", Value(1)).asInt();
     if (style != 1) die("only \"style\": 1 exists");
     Driver D;
     D.device = device;
     D.prefetch = prefetch;
-    return from_file(D, args, shard, nshards);
+    D.timing = timing;
+    const auto t_parsed = std::chrono::steady_clock::now();
+    const int rc = from_file(D, args, shard, nshards);
+    if (timing) {
+        const auto t_end = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "optflow_b200 timing: parse %.3f s, job %.3f s (waiting for decodes %.3f, staging %.3f, "
+                     "solves + outputs %.3f, look-ahead %.3f, match batches %.3f, setup %.3f, tail %.3f)\n",
+                     std::chrono::duration<double>(t_parsed - t_start).count(),
+                     std::chrono::duration<double>(t_end - t_parsed).count(), D.t_decode_wait, D.t_stage, D.t_solve,
+                     D.t_lookahead, D.t_points, D.t_setup, D.t_tail);
+    }
+    return rc;
 }
