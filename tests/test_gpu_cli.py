@@ -201,6 +201,31 @@ def test_sharded_random_points_cover_every_pair(gpu, tmp_path):
     assert [g["pId"] for g in json.load(open(job["matches_file"]))] == ["h0", "h1", "h2", "h4"]
 
 
+def test_run_job_launcher(gpu, tmp_path):
+    """python -m fibsem_optflow_b200.run_job: one driver process per rank, side by side (here both ranks on
+    device 0); the union of the ranks' outputs is the job's output"""
+    from fibsem_optflow_b200 import run_job
+    build_cli()
+    sl = synth.make_stack(4, 64, 96, seed=19)
+    names = []
+    for k, a in enumerate(sl):
+        p = str(tmp_path / ("g%d.png" % k))
+        write_png(p, a)
+        names.append(p)
+    images = [{"p": names[k], "q": names[k + 1], "pId": "g%d" % k, "qId": "g%d" % (k + 1),
+               "pGroupId": "%d.0" % k, "qGroupId": "%d.0" % (k + 1), "output_name": "g%d" % k} for k in range(4)]
+    job = {"debug": True, "output_type": "random_points", "scale": 1.0, "lambda": 0.15, "nscales": 2, "npoints": 3,
+           "rois": {"custom": [0, 0, 96, 64]}, "output_dir": str(tmp_path), "images": images}
+    jf = str(tmp_path / "job.json")
+    json.dump(job, open(jf, "w"))
+    assert run_job.run(jf, 2, devices=[0, 0]) == [0, 0]
+    seen = []
+    for f in sorted(f for f in os.listdir(str(tmp_path)) if f.startswith("point_matches_")):
+        assert "_r0of2_" in f or "_r1of2_" in f
+        seen += [g["pId"] for g in json.load(open(str(tmp_path / f)))]
+    assert sorted(seen) == ["g0", "g1", "g2", "g3"]
+
+
 def test_job_without_roi_is_prealigned(gpu, tmp_path):
     """N4: a pair without any roi is aligned by features first (src/optflow.cpp:366-377), its map moved by
     the same affine (:411-444), and its matches take the `features` branch of random_points (:544-550).

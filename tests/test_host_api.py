@@ -80,3 +80,19 @@ def test_sharding_world_size_2_gloo():
         assert p.exitcode == 0
     assert res[0][1] + res[1][1] == list(range(37))
     assert res[0][2] == res[1][2] == 2.0 and res[0][3] == res[1][3] == 37.0
+
+
+def test_run_job_commands():
+    """the multi-GPU job launcher: one driver process per GPU, contiguous shards, nothing shared"""
+    from fibsem_optflow_b200 import run_job
+    cs = run_job.commands("job.json", 4, devices=[2, 3, 0, 1], prefetch=6, timing=True)
+    assert len(cs) == 4
+    for r, c in enumerate(cs):
+        assert c[0].endswith("optflow_b200") and c[-1] == "job.json"
+        assert c[c.index("--shard") + 1] == "%d/4" % r
+        assert c[c.index("--device") + 1] == str([2, 3, 0, 1][r])
+        assert "--timing" in c and c[c.index("--prefetch") + 1] == "6"
+    import pytest
+    with pytest.raises(ValueError):
+        run_job.commands("job.json", 2, devices=[0])
+    assert run_job.main(["--gpus", "2", "--dry-run", "j.json"]) == 0
