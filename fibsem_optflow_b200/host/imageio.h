@@ -225,46 +225,61 @@ inline bool decode_pgm(const std::vector<uint8_t>& f, Gray8& img, std::string& e
 // (cv::imwrite's own TIFFs are LZW + predictor 2.)  16-bit samples keep their high byte, which is what
 // cv::imread(IMREAD_GRAYSCALE) returns for them.
 
-// TIFF-flavoured LZW: MSB-first codes of 9..12 bits, ClearCode 256, EOI 257, "early change"
+// TIFF-flavoured LZW: MSB-first codes of 9..12 bits, ClearCode 256, EOI 257, "early change".
+// A table entry is a position and a length in the OUTPUT: the string of a new code is the previous string plus one
+// byte, and those bytes were just written, one behind the other -- so a code is decoded by one forward copy and no
+// chain of prefixes is ever walked (a 4096^2 cv::imwrite TIFF of band-limited noise: 0.32 -> 0.19 s, libtiff: 0.20).
 inline bool tiff_lzw(const uint8_t* in, size_t n, std::vector<uint8_t>& out, size_t want)
 {
-    struct Entry { int prev; uint8_t first, last; uint16_t len; };
-    std::vector<Entry> tab(4096);
-    for (int i = 0; i < 256; i++) tab[i] = {-1, (uint8_t)i, (uint8_t)i, 1};
+    const size_t base = out.size();
+    out.resize(base + want + 8);                 // decoded in place; trimmed at the end
+    uint8_t* const o = out.data() + base;
+    uint32_t off[4096];
+    uint16_t len[4096];
     int next = 258, width = 9, prev = -1;
-    uint32_t acc = 0;
+    size_t prev_pos = 0, prev_len = 0, pos = 0, ip = 0;
+    uint64_t acc = 0;
     int bits = 0;
-    size_t pos = 0;
-    std::vector<uint8_t> tmp;
-    auto emit = [&](int code) {
-        const size_t len = tab[code].len, base = out.size();
-        out.resize(base + len);
-        for (size_t k = len; k-- > 0;) { out[base + k] = tab[code].last; code = tab[code].prev; }
-    };
-    while (out.size() < want) {
-        while (bits < width && pos < n) { acc = (acc << 8) | in[pos++]; bits += 8; }
+    bool ok = true;
+    while (pos < want) {
+        while (bits <= 56 && ip < n) { acc = (acc << 8) | in[ip++]; bits += 8; }
         if (bits < width) break;
         const int code = (int)((acc >> (bits - width)) & ((1u << width) - 1));
         bits -= width;
         if (code == 257) break;
         if (code == 256) { next = 258; width = 9; prev = -1; continue; }
-        if (prev < 0) {
-            if (code >= 256) return false;
-            emit(code);
-        } else if (code < next) {
-            emit(code);
-            if (next < 4096) { tab[next] = {prev, tab[prev].first, tab[code].first, (uint16_t)(tab[prev].len + 1)}; next++; }
-        } else if (code == next && next < 4096) {
-            tab[next] = {prev, tab[prev].first, tab[prev].first, (uint16_t)(tab[prev].len + 1)};
-            next++;
-            emit(code);
+        const size_t cur_pos = pos;
+        size_t cur_len;
+        if (code < 256) {
+            o[pos] = (uint8_t)code;
+            cur_len = 1;
+        } else if (code < next && prev >= 0) {
+            cur_len = len[code];
+            if (pos + cur_len > want + 8) cur_len = want + 8 - pos;
+            const uint8_t* src = o + off[code];
+            for (size_t k = 0; k < cur_len; k++) o[pos + k] = src[k];   // forward: source and target may overlap
+        } else if (code == next && prev >= 0 && next < 4096) {
+            cur_len = prev_len + 1;
+            if (pos + cur_len > want + 8) { ok = false; break; }
+            const uint8_t* src = o + prev_pos;
+            for (size_t k = 0; k < prev_len; k++) o[pos + k] = src[k];
+            o[pos + prev_len] = src[0];
         } else {
-            return false;
+            ok = false;
+            break;
         }
-        prev = code;
+        if (prev >= 0 && next < 4096) {
+            // string(next) = string(prev) + first byte of string(code): exactly the bytes at prev_pos .. prev_pos + prev_len
+            off[next] = (uint32_t)prev_pos;
+            len[next] = (uint16_t)(prev_len + 1 > 65535 ? 65535 : prev_len + 1);
+            next++;
+        }
+        pos += cur_len;
+        prev = code; prev_pos = cur_pos; prev_len = cur_len;
         if (next + 1 >= (1 << width) && width < 12) width++;   // early change
     }
-    return out.size() >= want;
+    out.resize(base + (pos < want ? pos : want));
+    return ok && pos >= want;
 }
 
 inline bool tiff_packbits(const uint8_t* in, size_t n, std::vector<uint8_t>& out, size_t want)
