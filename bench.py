@@ -205,6 +205,13 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def allmin(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return float(t.item())
+
     def allsum(x):
         if dist is None:
             return x
@@ -257,7 +264,9 @@ def run_ours(args):
     e1.record()
     barrier()
     sampler.mark_end()
-    ms_dev = allmax(e0.elapsed_time(e1))
+    ms_dev_own = e0.elapsed_time(e1)
+    ms_dev = allmax(ms_dev_own)
+    ms_dev_fastest = allmin(ms_dev_own)   # the spread over the ranks: a slow GPU (imbalance) or everybody (contention)?
     stats = solver.stats          # (overwritten by the later legs: keep what the line reports)
     levels = stats.level_sizes()
     iters_last = stats.iters_array().tolist()
@@ -383,12 +392,18 @@ def run_ours(args):
         barrier()
         t0 = time.perf_counter()
         r = run(mine, lo) if mine > 0 else None
+        ms_stack_own = (time.perf_counter() - t0) * 1e3     # this rank's own block, before it waits for the others
+        solve_own = sum(x.ms_total for x in r["stats"]) / max(mine, 1) if r else 0.0
         barrier()
         ms_stack = allmax((time.perf_counter() - t0) * 1e3)
+        ms_stack_fastest = allmin(ms_stack_own)
+        solve_slowest, solve_fastest = allmax(solve_own), allmin(solve_own)
         stack = {"workload": "configs[2]: stack of %d chained %dx%d pairs sharded by contiguous block over %d GPU(s), "
                              "5 scales, 5 warps, mask + 25 matches + flow download per pair" % (total, SS, SS, world),
                  "value": float(SS) * SS * total / (ms_stack * 1e-3) / 1e6, "unit": UNIT, "scaling": "strong",
                  "pairs_total": total, "pairs_per_gpu": mine, "ms_per_pair_per_gpu": ms_stack / max(mine, 1),
+                 "ms_per_pair_fastest_gpu": ms_stack_fastest / max(mine, 1),
+                 "solve_ms_per_pair": {"slowest_gpu": solve_slowest, "fastest_gpu": solve_fastest},
                  "h2d_bytes_per_pair": SS * SS, "d2h_bytes_per_pair": 8 * SS * SS,
                  "api": "tvl1_stack_run (pinned host buffers, copy streams)",
                  "iterations_first_pairs": [int(x.total_iterations) for x in (r["stats"][:4] if r else [])]}
@@ -451,6 +466,7 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": px_all / (ms_dev * 1e-3) / 1e6, "unit": UNIT,
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_dev / K,
+            "ms_per_step_fastest_gpu": ms_dev_fastest / K,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload(args),
             "e2e": {"value": px_all / (ms_e2e * 1e-3) / 1e6, "unit": UNIT,
