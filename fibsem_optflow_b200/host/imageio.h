@@ -260,10 +260,9 @@ inline bool tiff_lzw(const uint8_t* in, size_t n, std::vector<uint8_t>& out, siz
             for (size_t k = 0; k < cur_len; k++) o[pos + k] = src[k];   // forward: source and target may overlap
         } else if (code == next && prev >= 0 && next < 4096) {
             cur_len = prev_len + 1;
-            if (pos + cur_len > want + 8) { ok = false; break; }
+            if (pos + cur_len > want + 8) cur_len = want + 8 - pos;   // the strip's last string may run past what is wanted
             const uint8_t* src = o + prev_pos;
-            for (size_t k = 0; k < prev_len; k++) o[pos + k] = src[k];
-            o[pos + prev_len] = src[0];
+            for (size_t k = 0; k < cur_len; k++) o[pos + k] = k < prev_len ? src[k] : src[0];
         } else {
             ok = false;
             break;

@@ -59,7 +59,7 @@ def decode(tool, path):
     return np.frombuffer(body, np.uint8).reshape(h, w)
 
 
-@pytest.mark.parametrize("shape", [(37, 53), (128, 200), (1, 1), (5, 1000)])
+@pytest.mark.parametrize("shape", [(37, 53), (128, 200), (1, 1), (5, 1000), (300, 900)])
 def test_image_readers_match_cv2(tool, tmp_path, shape):
     cv2 = pytest.importorskip("cv2")
     from PIL import Image
